@@ -14,10 +14,11 @@
 //   phase1: every thread scans one "cell" of m consecutive samples (m | g) sequentially and
 //           produces its partial: sum d, d^2, d^3, d^4 (d = x - pivot, float64), min, max,
 //           line length and zero crossings inside the cell and across its right edge.
-//   phase2: cells -> block partials, written to a ring of the last TB + k + hop blocks.
+//   phase2: cells -> block partials, written to a ring of recent blocks.
 //   phase3: one thread per finished window combines k ring entries (direct sums for small k,
 //           differences of a running prefix for large k), turns the shifted power sums into
-//           central moments, and stores the requested feature columns.
+//           central moments, and stores the requested feature columns.  It is deferred until
+//           about half a CTA's worth of windows is pending so it is not a one-warp bubble.
 // Parity notes (SURVEY section 8c gotchas): population variance; kurtosis / skewness return 0 for a
 // constant window; zero is "not positive" for crossings; no partial tail window.
 #include "common.cuh"
@@ -26,11 +27,10 @@ namespace mhb {
 
 namespace {
 
-enum : int { Q_S1 = 0, Q_S2, Q_S3, Q_S4, Q_LL, Q_ZC, Q_LLB, Q_ZCB, Q_MN, Q_MX, NQ };
 constexpr int kThreads = 256;
 constexpr int kMaxFeat = 32;
 constexpr int kDirectK = 8;      // windows of <= kDirectK blocks are summed directly
-constexpr int kNAdd = 6;         // Q_S1..Q_ZC are additive and get a running prefix
+constexpr int kNPre = 6;         // S1..S4, LL, ZC get a running prefix when k > kDirectK
 
 struct StatsPlan {
     const void* x;
@@ -38,39 +38,98 @@ struct StatsPlan {
     int64_t nw, win_per_chunk;
     int32_t chunks_per_series;
     int32_t W, S, g, k, hop, m, cpb, TB, RB, NS;
+    int32_t flush;               // finalize once this many windows are pending
     int32_t stage_elems;
     int32_t use_tma;
     double th;
+    double inv_n;
     void* out;
     int64_t o_series, o_window, o_col;
     int32_t n_features;
     int32_t feat[kMaxFeat];
 };
 
+// Shared-memory partial record, structure-of-arrays.  The same layout serves the per-cell scratch
+// (n = cells per stage) and the block ring (n = RB).
+template <typename InT, bool M4, bool TD>
+struct Partials {
+    double* s1;
+    double* s2;
+    double* s3;
+    double* s4;
+    InT* mn;
+    InT* mx;
+    float* ll;     // line length inside + across the right edge
+    float* llb;    // ... the right-edge term alone
+    float* zc;     // zero crossings inside + across the right edge (exact small integers)
+    float* zcb;
+
+    __device__ unsigned char* carve(unsigned char* p, int n) {
+        s1 = reinterpret_cast<double*>(p); p += sizeof(double) * n;
+        s2 = reinterpret_cast<double*>(p); p += sizeof(double) * n;
+        s3 = s4 = nullptr;
+        if (M4) {
+            s3 = reinterpret_cast<double*>(p); p += sizeof(double) * n;
+            s4 = reinterpret_cast<double*>(p); p += sizeof(double) * n;
+        }
+        mn = reinterpret_cast<InT*>(p); p += sizeof(InT) * n;
+        mx = reinterpret_cast<InT*>(p); p += sizeof(InT) * n;
+        ll = llb = zc = zcb = nullptr;
+        if (TD) {
+            ll = reinterpret_cast<float*>(p); p += sizeof(float) * n;
+            llb = reinterpret_cast<float*>(p); p += sizeof(float) * n;
+            zc = reinterpret_cast<float*>(p); p += sizeof(float) * n;
+            zcb = reinterpret_cast<float*>(p); p += sizeof(float) * n;
+        }
+        return reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(p) + 15) & ~uintptr_t(15));
+    }
+};
+
+static size_t partial_bytes(size_t in_size, bool m4, bool td, int n) {
+    size_t b = (sizeof(double) * (m4 ? 4 : 2) + in_size * 2 + (td ? sizeof(float) * 4 : 0)) * n;
+    return ((b + 15) & ~size_t(15)) + 16;
+}
+
+template <typename T>
+__device__ __forceinline__ T tmin(T a, T b);
+template <>
+__device__ __forceinline__ float tmin<float>(float a, float b) { return fminf(a, b); }
+template <>
+__device__ __forceinline__ double tmin<double>(double a, double b) { return fmin(a, b); }
+template <typename T>
+__device__ __forceinline__ T tmax(T a, T b);
+template <>
+__device__ __forceinline__ float tmax<float>(float a, float b) { return fmaxf(a, b); }
+template <>
+__device__ __forceinline__ double tmax<double>(double a, double b) { return fmax(a, b); }
+
 template <typename InT>
 struct CellAcc {
     double s1 = 0, s2 = 0, s3 = 0, s4 = 0;
-    float ll = 0.f;
-    int zc = 0;
+    float ll = 0.f, zc = 0.f;
     InT mn, mx;
 };
 
-template <typename InT, bool M4, bool TD>
-__device__ __forceinline__ void accum(CellAcc<InT>& a, InT v, InT prev, bool has_prev, double c, InT th) {
+template <typename InT, bool M4>
+__device__ __forceinline__ void accum_moments(CellAcc<InT>& a, InT v, double c) {
     const double d = static_cast<double>(v) - c;
-    const double d2 = d * d;
     a.s1 += d;
-    a.s2 += d2;
+    a.s2 = fma(d, d, a.s2);
     if (M4) {
+        const double d2 = d * d;
         a.s3 = fma(d2, d, a.s3);
         a.s4 = fma(d2, d2, a.s4);
     }
-    a.mn = v < a.mn ? v : a.mn;
-    a.mx = v > a.mx ? v : a.mx;
-    if (TD && has_prev) {
-        a.ll += fabsf(static_cast<float>(v - prev));
-        a.zc += ((v > th) != (prev > th)) ? 1 : 0;
-    }
+    a.mn = tmin<InT>(a.mn, v);
+    a.mx = tmax<InT>(a.mx, v);
+}
+
+// time-domain pair terms between neighbours (prev, v); pos flags are 1.0f / 0.0f
+template <typename InT>
+__device__ __forceinline__ void accum_pair(CellAcc<InT>& a, InT v, InT prev, float pos, float pos_prev) {
+    a.ll += fabsf(static_cast<float>(v - prev));
+    const float dp = pos - pos_prev;
+    a.zc = fmaf(dp, dp, a.zc);
 }
 
 template <typename InT>
@@ -85,98 +144,102 @@ __device__ __forceinline__ double round_down_threshold<double>(double th) {
     return th;
 }
 
+// Stage geometry (no divisions in the stage loop).
+template <typename InT>
 struct StageDesc {
+    static constexpr int A = 16 / sizeof(InT);
     int64_t goff;       // global element offset of the stage's first sample
-    int64_t a0;         // aligned-down element offset the copy starts at
-    int32_t lead;       // goff - a0
+    int32_t lead;       // goff - aligned-down offset
     int32_t nblk;       // blocks in this stage
     int32_t cnt;        // samples belonging to blocks
     int32_t has_next;   // the sample after the stage exists in the series
     int32_t n_load;     // elements copied by TMA (multiple of 16 bytes)
     int32_t tma;        // stage is loaded by TMA (else cooperative guarded copy)
+
+    __device__ __forceinline__ void set(const StatsPlan& P, int64_t series_base, int64_t s0, int32_t blocks_left) {
+        nblk = blocks_left < P.TB ? blocks_left : P.TB;
+        cnt = nblk * P.g;
+        has_next = (s0 + cnt < P.series_len) ? 1 : 0;
+        goff = series_base + s0;
+        lead = static_cast<int32_t>(goff & (A - 1));
+        n_load = (lead + cnt + has_next + A - 1) & ~(A - 1);
+        tma = (P.use_tma && (goff - lead) + n_load <= P.total_elems) ? 1 : 0;
+    }
 };
 
-template <typename InT>
-__device__ __forceinline__ StageDesc describe_stage(const StatsPlan& P, int64_t series, int64_t blk_begin,
-                                                    int32_t n_blocks, int32_t st) {
-    constexpr int A = 16 / sizeof(InT);
-    StageDesc d;
-    const int32_t b0 = st * P.TB;
-    d.nblk = min(P.TB, n_blocks - b0);
-    d.cnt = d.nblk * P.g;
-    const int64_t s0 = (blk_begin + b0) * static_cast<int64_t>(P.g);
-    d.has_next = (s0 + d.cnt < P.series_len) ? 1 : 0;
-    d.goff = series * P.series_stride + s0;
-    d.a0 = d.goff & ~static_cast<int64_t>(A - 1);
-    d.lead = static_cast<int32_t>(d.goff - d.a0);
-    d.n_load = (d.lead + d.cnt + d.has_next + A - 1) & ~(A - 1);
-    d.tma = (P.use_tma && d.a0 + d.n_load <= P.total_elems) ? 1 : 0;
-    return d;
-}
+__device__ __forceinline__ int wrap(int i, int n) { return i >= n ? i - n : i; }
 
 // ---------------------------------------------------------------------------------------------
-template <typename InT, typename OutT, bool M4, bool TD, int MCELL /*0 = runtime m*/>
-__global__ void __launch_bounds__(kThreads, 2) window_stats_kernel(const StatsPlan P) {
+template <typename InT, typename OutT, bool M4, bool TD, int MCELL /*0 = runtime m; -8 = 2 x float4*/>
+__global__ void __launch_bounds__(kThreads, 3) window_stats_kernel(const StatsPlan P) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int tid = threadIdx.x;
-    const int m = MCELL ? MCELL : P.m;
+    const int m = MCELL > 0 ? MCELL : (MCELL < 0 ? -MCELL : P.m);
+    using Part = Partials<InT, M4, TD>;
 
     // ---- carve shared memory
     uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);                 // NS barriers (<= 8)
     unsigned char* ptr = smem_raw + 128;
     InT* stage_buf = reinterpret_cast<InT*>(ptr);
     ptr += static_cast<size_t>(P.NS) * P.stage_elems * sizeof(InT);
-    ptr = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(ptr) + 15) & ~uintptr_t(15));
     const int ncell_max = P.TB * P.cpb;
-    double* cell = reinterpret_cast<double*>(ptr);                          // [NQ][ncell_max] (cpb > 1)
-    if (P.cpb > 1) ptr += sizeof(double) * NQ * ncell_max;
-    double* ring = reinterpret_cast<double*>(ptr);                          // [NQ][RB]
-    ptr += sizeof(double) * NQ * P.RB;
-    double* pre = reinterpret_cast<double*>(ptr);                           // [kNAdd][RB + 1] (k > kDirectK)
-    __shared__ double carry[kNAdd];
+    Part cell, ring;
+    if (P.cpb > 1) ptr = cell.carve(ptr, ncell_max);
+    ptr = ring.carve(ptr, P.RB);
+    double* pre = reinterpret_cast<double*>(ptr);                           // [kNPre][RB + 1] (k > kDirectK)
+    const int R1 = P.RB + 1;
+    __shared__ double carry[kNPre];
 
     // ---- which chunk
     const int64_t series = blockIdx.x / P.chunks_per_series;
-    const int32_t chunk = blockIdx.x % P.chunks_per_series;
+    const int32_t chunk = blockIdx.x - static_cast<int32_t>(series) * P.chunks_per_series;
     const int64_t w0 = static_cast<int64_t>(chunk) * P.win_per_chunk;
     const int64_t w1 = min(P.nw, w0 + P.win_per_chunk);
     const int32_t nwin = static_cast<int32_t>(w1 - w0);
-    const int64_t blk_begin = w0 * P.hop;
     const int32_t n_blocks = (nwin - 1) * P.hop + P.k;
     const int32_t n_stages = (n_blocks + P.TB - 1) / P.TB;
     const bool use_prefix = P.k > kDirectK;
     const InT* xg = reinterpret_cast<const InT*>(P.x);
+    const int64_t series_base = series * P.series_stride;
+    const int64_t chunk_s0 = w0 * P.S;                    // first sample of the chunk (series-relative)
+    const int32_t stage_samples = P.TB * P.g;
 
     if (tid == 0) {
         for (int i = 0; i < P.NS; ++i) mbar_init(&full[i], 1);
         fence_barrier_init();
     }
-    if (tid < kNAdd) carry[tid] = 0.0;
-    if (use_prefix && tid < kNAdd) pre[tid * (P.RB + 1)] = 0.0;           // prefix before block 0
+    if (tid < kNPre) carry[tid] = 0.0;
+    if (use_prefix && tid < kNPre) pre[tid * R1] = 0.0;                    // prefix before block 0
     __syncthreads();
 
     if (tid == 0) {
         for (int st = 0; st < P.NS && st < n_stages; ++st) {
-            const StageDesc d = describe_stage<InT>(P, series, blk_begin, n_blocks, st);
+            StageDesc<InT> d;
+            d.set(P, series_base, chunk_s0 + static_cast<int64_t>(st) * stage_samples, n_blocks - st * P.TB);
             if (d.tma) {
                 mbar_arrive_expect_tx(&full[st], d.n_load * sizeof(InT));
-                bulk_g2s(stage_buf + static_cast<size_t>(st) * P.stage_elems, xg + d.a0, d.n_load * sizeof(InT),
-                         &full[st]);
+                bulk_g2s(stage_buf + static_cast<size_t>(st) * P.stage_elems, xg + (d.goff - d.lead),
+                         d.n_load * sizeof(InT), &full[st]);
             }
         }
     }
 
     const InT th = round_down_threshold<InT>(P.th > 0.0 ? P.th : 0.0);
-    double c = 0.0;            // pivot of the shifted power sums: first sample of the chunk
-    int32_t blocks_done = 0;
-    int32_t emitted = 0;
+    double c = 0.0;             // pivot of the shifted power sums: first sample of the chunk
+    int32_t blocks_done = 0;    // blocks whose partials are in the ring
+    int32_t ring_head = 0;      // ring slot of block `blocks_done`
+    int32_t emitted = 0;        // windows already written
+    int32_t ring_emit = 0;      // ring slot of the first block of window `emitted`
+    int32_t pre_emit = 0;       // prefix slot of that block
+    int slot = 0;
+    uint32_t parity = 0;
 
     for (int st = 0; st < n_stages; ++st) {
-        const int slot = st % P.NS;
-        const StageDesc d = describe_stage<InT>(P, series, blk_begin, n_blocks, st);
+        StageDesc<InT> d;
+        d.set(P, series_base, chunk_s0 + static_cast<int64_t>(st) * stage_samples, n_blocks - st * P.TB);
         InT* buf = stage_buf + static_cast<size_t>(slot) * P.stage_elems;
         if (d.tma) {
-            mbar_wait(&full[slot], (st / P.NS) & 1);
+            mbar_wait(&full[slot], parity);
         } else {
             // guarded cooperative copy: unaligned base pointer or the last few samples of the buffer
             const int n = d.cnt + d.has_next;
@@ -191,81 +254,145 @@ __global__ void __launch_bounds__(kThreads, 2) window_stats_kernel(const StatsPl
         for (int ce = tid; ce < ncell; ce += kThreads) {
             const InT* p = s + ce * m;
             CellAcc<InT> a;
-            a.mn = p[0];
-            a.mx = p[0];
             InT prev = p[0];
-            accum<InT, M4, TD>(a, prev, prev, false, c, th);
-            if (MCELL) {
+            a.mn = prev;
+            a.mx = prev;
+            float pos_prev = (TD && prev > th) ? 1.f : 0.f;
+            accum_moments<InT, M4>(a, prev, c);
+            if (MCELL < 0) {
+                // power-of-two blocks: the cell is -MCELL/4 aligned 128-bit shared loads
+                InT vv[MCELL < 0 ? -MCELL : 1];
 #pragma unroll
-                for (int i = 1; i < (MCELL ? MCELL : 1); ++i) {
+                for (int i = 0; i < (MCELL < 0 ? -MCELL : 0) / 4; ++i) {
+                    const float4 q = reinterpret_cast<const float4*>(p)[i];
+                    vv[4 * i + 0] = static_cast<InT>(q.x);
+                    vv[4 * i + 1] = static_cast<InT>(q.y);
+                    vv[4 * i + 2] = static_cast<InT>(q.z);
+                    vv[4 * i + 3] = static_cast<InT>(q.w);
+                }
+#pragma unroll
+                for (int i = 1; i < (MCELL < 0 ? -MCELL : 1); ++i) {
+                    const InT v = vv[i];
+                    accum_moments<InT, M4>(a, v, c);
+                    if (TD) {
+                        const float pos = v > th ? 1.f : 0.f;
+                        accum_pair<InT>(a, v, prev, pos, pos_prev);
+                        pos_prev = pos;
+                    }
+                    prev = v;
+                }
+            } else if (MCELL > 0) {
+#pragma unroll
+                for (int i = 1; i < (MCELL > 0 ? MCELL : 1); ++i) {
                     const InT v = p[i];
-                    accum<InT, M4, TD>(a, v, prev, true, c, th);
+                    accum_moments<InT, M4>(a, v, c);
+                    if (TD) {
+                        const float pos = v > th ? 1.f : 0.f;
+                        accum_pair<InT>(a, v, prev, pos, pos_prev);
+                        pos_prev = pos;
+                    }
                     prev = v;
                 }
             } else {
 #pragma unroll 4
                 for (int i = 1; i < m; ++i) {
                     const InT v = p[i];
-                    accum<InT, M4, TD>(a, v, prev, true, c, th);
+                    accum_moments<InT, M4>(a, v, c);
+                    if (TD) {
+                        const float pos = v > th ? 1.f : 0.f;
+                        accum_pair<InT>(a, v, prev, pos, pos_prev);
+                        pos_prev = pos;
+                    }
                     prev = v;
                 }
             }
-            double llb = 0.0, zcb = 0.0;
+            float llb = 0.f, zcb = 0.f;
             if (TD && (ce + 1 < ncell || d.has_next)) {
                 const InT nx = p[m];
                 llb = fabsf(static_cast<float>(nx - prev));
-                zcb = ((nx > th) != (prev > th)) ? 1.0 : 0.0;
+                zcb = ((nx > th) != (prev > th)) ? 1.f : 0.f;
             }
-            double* dst;
-            int idx, stride;
-            if (P.cpb > 1) {
-                dst = cell; idx = ce; stride = ncell_max;
-            } else {
-                dst = ring; idx = (blocks_done + ce) % P.RB; stride = P.RB;
+            const Part& dst = (P.cpb > 1) ? cell : ring;
+            const int idx = (P.cpb > 1) ? ce : wrap(ring_head + ce, P.RB);
+            dst.s1[idx] = a.s1;
+            dst.s2[idx] = a.s2;
+            if (M4) {
+                dst.s3[idx] = a.s3;
+                dst.s4[idx] = a.s4;
             }
-            dst[Q_S1 * stride + idx] = a.s1;
-            dst[Q_S2 * stride + idx] = a.s2;
-            dst[Q_S3 * stride + idx] = a.s3;
-            dst[Q_S4 * stride + idx] = a.s4;
-            dst[Q_LL * stride + idx] = static_cast<double>(a.ll) + llb;      // "full": inside + right edge
-            dst[Q_ZC * stride + idx] = static_cast<double>(a.zc) + zcb;
-            dst[Q_LLB * stride + idx] = llb;
-            dst[Q_ZCB * stride + idx] = zcb;
-            dst[Q_MN * stride + idx] = static_cast<double>(a.mn);
-            dst[Q_MX * stride + idx] = static_cast<double>(a.mx);
+            dst.mn[idx] = a.mn;
+            dst.mx[idx] = a.mx;
+            if (TD) {
+                dst.ll[idx] = a.ll + llb;
+                dst.llb[idx] = llb;
+                dst.zc[idx] = a.zc + zcb;
+                dst.zcb[idx] = zcb;
+            }
         }
         __syncthreads();      // stage buffer fully consumed; cell partials visible
 
         // ---------------- refill this slot with stage st + NS
         if (tid == 0 && st + P.NS < n_stages) {
-            const StageDesc nd = describe_stage<InT>(P, series, blk_begin, n_blocks, st + P.NS);
+            StageDesc<InT> nd;
+            nd.set(P, series_base, chunk_s0 + static_cast<int64_t>(st + P.NS) * stage_samples,
+                   n_blocks - (st + P.NS) * P.TB);
             if (nd.tma) {
                 mbar_arrive_expect_tx(&full[slot], nd.n_load * sizeof(InT));
-                bulk_g2s(buf, xg + nd.a0, nd.n_load * sizeof(InT), &full[slot]);
+                bulk_g2s(buf, xg + (nd.goff - nd.lead), nd.n_load * sizeof(InT), &full[slot]);
             }
         }
+        if (++slot == P.NS) {
+            slot = 0;
+            parity ^= 1;
+        }
 
-        // ---------------- phase 2: cells -> blocks (quantity-major so warps stay uniform)
+        // ---------------- phase 2: cells -> blocks; one (block, quantity pair) per thread
         if (P.cpb > 1) {
-            const int total = d.nblk * NQ;
+            constexpr int NG = 2 + (M4 ? 1 : 0) + (TD ? 2 : 0);     // {s1,s2} {mn,mx} [{s3,s4}] [{ll,llb} {zc,zcb}]
+            const int total = d.nblk * NG;
             for (int idx = tid; idx < total; idx += kThreads) {
-                const int q = idx / d.nblk;
-                const int b = idx - q * d.nblk;
-                const double* src = cell + q * ncell_max + b * P.cpb;
-                double r;
-                if (q <= Q_ZC) {
-                    r = 0.0;
-                    for (int i = 0; i < P.cpb; ++i) r += src[i];
-                } else if (q <= Q_ZCB) {
-                    r = src[P.cpb - 1];
-                } else if (q == Q_MN) {
-                    r = src[0];
-                    for (int i = 1; i < P.cpb; ++i) r = fmin(r, src[i]);
-                } else {
-                    r = src[0];
-                    for (int i = 1; i < P.cpb; ++i) r = fmax(r, src[i]);
+                int grp = 0, b = idx;
+                while (b >= d.nblk) {
+                    b -= d.nblk;
+                    ++grp;
                 }
-                ring[q * P.RB + (blocks_done + b) % P.RB] = r;
+                const int c0 = b * P.cpb;
+                const int r = wrap(ring_head + b, P.RB);
+                if (grp == 0) {
+                    double u = 0, v = 0;
+                    for (int i = 0; i < P.cpb; ++i) {
+                        u += cell.s1[c0 + i];
+                        v += cell.s2[c0 + i];
+                    }
+                    ring.s1[r] = u;
+                    ring.s2[r] = v;
+                } else if (grp == 1) {
+                    InT u = cell.mn[c0], v = cell.mx[c0];
+                    for (int i = 1; i < P.cpb; ++i) {
+                        u = tmin<InT>(u, cell.mn[c0 + i]);
+                        v = tmax<InT>(v, cell.mx[c0 + i]);
+                    }
+                    ring.mn[r] = u;
+                    ring.mx[r] = v;
+                } else if (M4 && grp == 2) {
+                    double u = 0, v = 0;
+                    for (int i = 0; i < P.cpb; ++i) {
+                        u += cell.s3[c0 + i];
+                        v += cell.s4[c0 + i];
+                    }
+                    ring.s3[r] = u;
+                    ring.s4[r] = v;
+                } else if (TD && grp == (M4 ? 3 : 2)) {
+                    double u = 0;                    // float cell terms, float64 across cells
+                    for (int i = 0; i < P.cpb; ++i) u += static_cast<double>(cell.ll[c0 + i]);
+                    ring.ll[r] = static_cast<float>(u);
+                    ring.llb[r] = cell.llb[c0 + P.cpb - 1];
+                } else if (TD) {
+                    float u = 0;
+                    for (int i = 0; i < P.cpb; ++i) u += cell.zc[c0 + i];
+                    ring.zc[r] = u;
+                    ring.zcb[r] = cell.zcb[c0 + P.cpb - 1];
+                }
             }
             __syncthreads();
         }
@@ -273,128 +400,171 @@ __global__ void __launch_bounds__(kThreads, 2) window_stats_kernel(const StatsPl
         // ---------------- running prefix of the additive quantities (large k only)
         if (use_prefix) {
             const int warp = tid >> 5, lane = tid & 31;
-            if (warp == (st & 7)) {                 // rotate the serial work over the SM sub-partitions
-                for (int q = 0; q < kNAdd; ++q) {
-                    double run = carry[q];
-                    for (int base = 0; base < d.nblk; base += 32) {
-                        const int b = base + lane;
-                        double v = (b < d.nblk) ? ring[q * P.RB + (blocks_done + b) % P.RB] : 0.0;
-#pragma unroll
-                        for (int o = 1; o < 32; o <<= 1) {
-                            const double u = __shfl_up_sync(0xffffffffu, v, o);
-                            if (lane >= o) v += u;
-                        }
-                        if (b < d.nblk) pre[q * (P.RB + 1) + (blocks_done + b + 1) % (P.RB + 1)] = run + v;
-                        run += __shfl_sync(0xffffffffu, v, 31);
+            constexpr int nq = 2 + (M4 ? 2 : 0) + (TD ? 2 : 0);
+            if (warp < nq) {                        // one warp per additive quantity
+                // quantity order: s1, s2, [s3, s4], [ll, zc]
+                const int q = warp;
+                const bool is_f = TD && q >= nq - 2;
+                const double* srcd = q == 0 ? ring.s1 : q == 1 ? ring.s2 : (M4 && q == 2) ? ring.s3 : ring.s4;
+                const float* srcf = (q == nq - 2) ? ring.ll : ring.zc;
+                double run = carry[q];
+                int pslot = (pre_emit + (blocks_done - emitted * P.hop)) % R1;   // prefix slot of block blocks_done
+                if (pslot < 0) pslot += R1;
+                for (int base = 0; base < d.nblk; base += 32) {
+                    const int b = base + lane;
+                    double v = 0.0;
+                    if (b < d.nblk) {
+                        const int r = wrap(ring_head + b, P.RB);
+                        v = is_f ? static_cast<double>(srcf[r]) : srcd[r];
                     }
-                    __syncwarp();
-                    if (lane == 0) carry[q] = run;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const double u = __shfl_up_sync(0xffffffffu, v, o);
+                        if (lane >= o) v += u;
+                    }
+                    if (b < d.nblk) pre[q * R1 + wrap(pslot + b + 1, R1)] = run + v;
+                    run += __shfl_sync(0xffffffffu, v, 31);
                 }
+                if (lane == 0) carry[q] = run;
             }
             __syncthreads();
         }
         blocks_done += d.nblk;
+        ring_head = wrap(ring_head + d.nblk, P.RB);
 
-        // ---------------- phase 3: finished windows
+        // ---------------- phase 3: finished windows (deferred until `flush` are pending)
         int32_t ready = 0;
-        if (blocks_done >= P.k) ready = min(nwin, (blocks_done - P.k) / P.hop + 1);
-        for (int wl = emitted + tid; wl < ready; wl += kThreads) {
-            const int b0 = wl * P.hop;
-            double S1, S2, S3 = 0, S4 = 0, LL = 0, ZC = 0;
-            const int last = (b0 + P.k - 1) % P.RB;
-            if (!use_prefix) {
-                S1 = S2 = 0.0;
-                for (int j = 0; j < P.k; ++j) {
-                    const int r = (b0 + j) % P.RB;
-                    S1 += ring[Q_S1 * P.RB + r];
-                    S2 += ring[Q_S2 * P.RB + r];
+        if (blocks_done >= P.k) {
+            ready = (blocks_done - P.k) / P.hop + 1;
+            ready = ready < nwin ? ready : nwin;
+        }
+        const bool do_flush = (ready - emitted >= P.flush) || (st == n_stages - 1);
+        if (do_flush) {
+            constexpr int nq = 2 + (M4 ? 2 : 0) + (TD ? 2 : 0);
+            for (int wl = emitted + tid; wl < ready; wl += kThreads) {
+                const int rel = (wl - emitted) * P.hop;          // < RB by construction
+                const int r0 = wrap(ring_emit + rel, P.RB);
+                double S1, S2, S3 = 0, S4 = 0, LL = 0, ZC = 0;
+                InT mn = ring.mn[r0], mx = ring.mx[r0];
+                int r = r0;
+                if (!use_prefix) {
+                    S1 = ring.s1[r0];
+                    S2 = ring.s2[r0];
                     if (M4) {
-                        S3 += ring[Q_S3 * P.RB + r];
-                        S4 += ring[Q_S4 * P.RB + r];
+                        S3 = ring.s3[r0];
+                        S4 = ring.s4[r0];
                     }
                     if (TD) {
-                        LL += ring[Q_LL * P.RB + r];
-                        ZC += ring[Q_ZC * P.RB + r];
+                        LL = ring.ll[r0];
+                        ZC = ring.zc[r0];
+                    }
+                    for (int j = 1; j < P.k; ++j) {
+                        r = wrap(r + 1, P.RB);
+                        S1 += ring.s1[r];
+                        S2 += ring.s2[r];
+                        if (M4) {
+                            S3 += ring.s3[r];
+                            S4 += ring.s4[r];
+                        }
+                        if (TD) {
+                            LL += ring.ll[r];
+                            ZC += ring.zc[r];
+                        }
+                        mn = tmin<InT>(mn, ring.mn[r]);
+                        mx = tmax<InT>(mx, ring.mx[r]);
+                    }
+                } else {
+                    const int lo = wrap(pre_emit + rel, R1);
+                    int hi = lo + P.k;
+                    while (hi >= R1) hi -= R1;
+                    S1 = pre[0 * R1 + hi] - pre[0 * R1 + lo];
+                    S2 = pre[1 * R1 + hi] - pre[1 * R1 + lo];
+                    if (M4) {
+                        S3 = pre[2 * R1 + hi] - pre[2 * R1 + lo];
+                        S4 = pre[3 * R1 + hi] - pre[3 * R1 + lo];
+                    }
+                    if (TD) {
+                        LL = pre[(nq - 2) * R1 + hi] - pre[(nq - 2) * R1 + lo];
+                        ZC = pre[(nq - 1) * R1 + hi] - pre[(nq - 1) * R1 + lo];
+                    }
+                    for (int j = 1; j < P.k; ++j) {
+                        r = wrap(r + 1, P.RB);
+                        mn = tmin<InT>(mn, ring.mn[r]);
+                        mx = tmax<InT>(mx, ring.mx[r]);
                     }
                 }
-            } else {
-                const int R1 = P.RB + 1;
-                const int hi = (b0 + P.k) % R1, lo = b0 % R1;
-                S1 = pre[Q_S1 * R1 + hi] - pre[Q_S1 * R1 + lo];
-                S2 = pre[Q_S2 * R1 + hi] - pre[Q_S2 * R1 + lo];
-                if (M4) {
-                    S3 = pre[Q_S3 * R1 + hi] - pre[Q_S3 * R1 + lo];
-                    S4 = pre[Q_S4 * R1 + hi] - pre[Q_S4 * R1 + lo];
+                if (TD) {       // the right edge of the last block belongs to the next window only
+                    LL -= ring.llb[r];
+                    ZC -= ring.zcb[r];
                 }
-                if (TD) {
-                    LL = pre[Q_LL * R1 + hi] - pre[Q_LL * R1 + lo];
-                    ZC = pre[Q_ZC * R1 + hi] - pre[Q_ZC * R1 + lo];
-                }
-            }
-            if (TD) {
-                LL -= ring[Q_LLB * P.RB + last];
-                ZC -= ring[Q_ZCB * P.RB + last];
-            }
-            double mn = ring[Q_MN * P.RB + b0 % P.RB], mx = ring[Q_MX * P.RB + b0 % P.RB];
-            for (int j = 1; j < P.k; ++j) {
-                const int r = (b0 + j) % P.RB;
-                mn = fmin(mn, ring[Q_MN * P.RB + r]);
-                mx = fmax(mx, ring[Q_MX * P.RB + r]);
-            }
 
-            // shifted power sums -> central moments
-            const double n = static_cast<double>(P.W);
-            const double dl = S1 / n;
-            const double mean = c + dl;
-            double M2 = S2 - S1 * dl;
-            if (M2 < 0.0 || mn == mx) M2 = 0.0;        // constant window: exactly zero, like the two-pass form
-            const double var = M2 / n;
-            const double sd = sqrt(var);
-            double skew = 0.0, kurt = 0.0;
-            if (M4 && var > 0.0) {
-                const double M3 = S3 - 3.0 * dl * S2 + 2.0 * n * dl * dl * dl;
-                const double M4v = S4 - 4.0 * dl * S3 + 6.0 * dl * dl * S2 - 3.0 * n * dl * dl * dl * dl;
-                skew = (M3 / n) / (sd * sd * sd);
-                kurt = (M4v / n) / (var * var);
-            }
-            const int64_t obase = series * P.o_series + (w0 + wl) * P.o_window;
-            for (int j = 0; j < P.n_features; ++j) {
-                double v;
-                switch (P.feat[j]) {
-                    case MHB_F_MEAN: v = mean; break;
-                    case MHB_F_VAR:
-                    case MHB_F_HJORTH_ACTIVITY: v = var; break;
-                    case MHB_F_STD: v = sd; break;
-                    case MHB_F_MIN: v = mn; break;
-                    case MHB_F_MAX: v = mx; break;
-                    case MHB_F_DRANGE: v = mx - mn; break;
-                    case MHB_F_SKEWNESS: v = skew; break;
-                    case MHB_F_KURTOSIS: v = kurt; break;
-                    case MHB_F_KURTOSIS_EXCESS: v = kurt - 3.0; break;
-                    case MHB_F_COEFF_VAR: v = sd / mean; break;
-                    case MHB_F_ZERO_CROSSINGS: v = ZC; break;
-                    case MHB_F_LINE_LENGTH: v = LL; break;
-                    case MHB_F_SUM: v = mean * n; break;
-                    default: v = 0.0; break;
+                // shifted power sums -> central moments
+                const double n = static_cast<double>(P.W);
+                const double dl = S1 * P.inv_n;
+                const double mean = c + dl;
+                double M2 = S2 - S1 * dl;
+                if (M2 < 0.0 || mn == mx) M2 = 0.0;     // constant window: exactly zero, like the two-pass form
+                const double var = M2 * P.inv_n;
+                const double sd = sqrt(var);
+                double skew = 0.0, kurt = 0.0;
+                if (M4 && var > 0.0) {
+                    const double dl2 = dl * dl;
+                    const double M3 = S3 - 3.0 * dl * S2 + 2.0 * n * dl2 * dl;
+                    const double M4v = S4 - 4.0 * dl * S3 + 6.0 * dl2 * S2 - 3.0 * n * dl2 * dl2;
+                    const double inv_var = 1.0 / var;
+                    skew = (M3 * P.inv_n) * inv_var / sd;
+                    kurt = (M4v * P.inv_n) * inv_var * inv_var;
                 }
-                store_cell<OutT>(P.out, obase + j * P.o_col, v);
+                const int64_t obase = series * P.o_series + (w0 + wl) * P.o_window;
+                for (int j = 0; j < P.n_features; ++j) {
+                    double v;
+                    switch (P.feat[j]) {
+                        case MHB_F_MEAN: v = mean; break;
+                        case MHB_F_VAR:
+                        case MHB_F_HJORTH_ACTIVITY: v = var; break;
+                        case MHB_F_STD: v = sd; break;
+                        case MHB_F_MIN: v = static_cast<double>(mn); break;
+                        case MHB_F_MAX: v = static_cast<double>(mx); break;
+                        case MHB_F_DRANGE: v = static_cast<double>(mx) - static_cast<double>(mn); break;
+                        case MHB_F_SKEWNESS: v = skew; break;
+                        case MHB_F_KURTOSIS: v = kurt; break;
+                        case MHB_F_KURTOSIS_EXCESS: v = kurt - 3.0; break;
+                        case MHB_F_COEFF_VAR: v = sd / mean; break;
+                        case MHB_F_ZERO_CROSSINGS: v = ZC; break;
+                        case MHB_F_LINE_LENGTH: v = LL; break;
+                        case MHB_F_SUM: v = mean * n; break;
+                        default: v = 0.0; break;
+                    }
+                    store_cell<OutT>(P.out, obase + j * P.o_col, v);
+                }
             }
+            const int adv = (ready - emitted) * P.hop;       // blocks released (may exceed RB when hop > k)
+            ring_emit = (ring_emit + adv) % P.RB;
+            pre_emit = (pre_emit + adv) % R1;
+            emitted = ready;
         }
-        emitted = ready > emitted ? ready : emitted;
-        // no barrier needed here: the next iteration only writes ring / prefix entries of NEW blocks,
-        // which never alias entries a still-pending window of this iteration reads (RB >= TB+k+hop+1),
-        // and its first block-level write happens after the barrier that follows phase 1.
-        if (P.cpb == 1) __syncthreads();   // ...except when phase 1 itself writes the ring
+        // The next iteration writes ring / prefix slots of NEW blocks only after a barrier that every
+        // thread reaches after finishing this phase (cpb > 1: the barrier after phase 1); when phase 1
+        // itself writes the ring, close the iteration with one.
+        if (P.cpb == 1) __syncthreads();
     }
 }
 
 // ---------------------------------------------------------------------------------------------
 struct CellChoice {
     int m;
-    int mcell_template;   // 0 = runtime
+    int mcell_template;   // 0 = runtime, >0 unrolled scalar cell, <0 float4 cell
 };
 
-CellChoice choose_cell(int64_t g) {
+CellChoice choose_cell(int64_t g, bool allow_vec4) {
+    CellChoice c;
+    if (allow_vec4 && g % 8 == 0) {
+        // power-of-two-ish blocks have no odd divisor: 2 x 128-bit loads per thread (lane stride 32 B:
+        // 2-way conflict on LDS.128, harmless at 4 B/sample of demand)
+        c.m = 8;
+        c.mcell_template = -8;
+        return c;
+    }
     // scalar shared-memory reads at a lane stride of m words: conflict degree gcd(m, 32)
     int best = 1, best_score = -1;
     for (int m = 1; m <= 32; ++m) {
@@ -407,9 +577,8 @@ CellChoice choose_cell(int64_t g) {
             best = m;
         }
     }
-    CellChoice c;
     c.m = best;
-    c.mcell_template = (best == 25 || best == 8 || best == 16 || best == 32) ? best : 0;
+    c.mcell_template = (best == 25) ? best : 0;
     return c;
 }
 
@@ -423,13 +592,11 @@ cudaError_t launch_with_cell(const StatsPlan& P, int mt, dim3 grid, size_t smem,
         kern<<<grid, kThreads, smem, stream>>>(P);                                                      \
         return cudaGetLastError();                                                                      \
     }
-    switch (mt) {
-        case 25: MHB_LAUNCH(25)
-        case 8: MHB_LAUNCH(8)
-        case 16: MHB_LAUNCH(16)
-        case 32: MHB_LAUNCH(32)
-        default: MHB_LAUNCH(0)
+    if (mt == -8) {
+        if constexpr (sizeof(InT) == 4) MHB_LAUNCH(-8)
     }
+    if (mt == 25) MHB_LAUNCH(25)
+    MHB_LAUNCH(0)
 #undef MHB_LAUNCH
 }
 
@@ -466,6 +633,7 @@ int32_t window_stats_impl(const InT* x, const mhb_windows* geom, const int32_t* 
     P.W = geom->wsize;
     P.S = geom->wstep;
     P.th = zc_threshold;
+    P.inv_n = 1.0 / static_cast<double>(geom->wsize);
     P.out = table->out;
     P.o_series = table->series_stride;
     P.o_window = table->window_stride;
@@ -473,7 +641,7 @@ int32_t window_stats_impl(const InT* x, const mhb_windows* geom, const int32_t* 
 
     // block size: a divisor of gcd(W, S) small enough for one stage, with k + hop bounded
     int64_t g = gcd64(P.W, P.S);
-    constexpr int64_t kMaxStageBytes = 32 * 1024;
+    constexpr int64_t kMaxStageBytes = 24 * 1024;
     const int64_t max_block = kMaxStageBytes / static_cast<int64_t>(sizeof(InT));
     if (g > max_block) {
         int64_t best = 1;
@@ -486,37 +654,46 @@ int32_t window_stats_impl(const InT* x, const mhb_windows* geom, const int32_t* 
     }
     P.g = static_cast<int32_t>(g);
     const int64_t k64 = P.W / g, hop64 = P.S / g;
-    MHB_REQUIRE(k64 + hop64 <= 4096, MHB_E_UNSUPPORTED,
-                "window_stats: wsize=%d wstep=%d needs %lld + %lld blocks per window/hop (> 4096); "
-                "use the large-window path",
-                P.W, P.S, (long long)k64, (long long)hop64);
+    MHB_REQUIRE(k64 + hop64 <= 1024, MHB_E_UNSUPPORTED,
+                "window_stats: wsize=%d wstep=%d needs %lld + %lld blocks per window/hop (> 1024)", P.W, P.S,
+                (long long)k64, (long long)hop64);
     P.k = static_cast<int32_t>(k64);
     P.hop = static_cast<int32_t>(hop64);
-    const CellChoice cc = choose_cell(g);
+    const CellChoice cc = choose_cell(g, sizeof(InT) == 4 && geom->series_stride % 4 == 0);
     P.m = cc.m;
     P.cpb = static_cast<int32_t>(g / cc.m);
     int64_t tb = P.cpb <= kThreads ? kThreads / P.cpb : 1;
-    tb = tb < kMaxStageBytes / static_cast<int64_t>(g * sizeof(InT)) ? tb : kMaxStageBytes / (g * sizeof(InT));
+    const int64_t tb_cap = kMaxStageBytes / static_cast<int64_t>(g * sizeof(InT));
+    if (tb > tb_cap) tb = tb_cap;
     if (tb < 1) tb = 1;
-    if (tb > 256) tb = 256;
     P.TB = static_cast<int32_t>(tb);
-    P.RB = P.TB + P.k + P.hop + 1;
-    P.NS = 3;
+    // deferred finalisation: let about half a CTA of windows pile up before phase 3 runs
+    {
+        const int64_t per_stage = P.TB / P.hop + 1;
+        int64_t flush = kThreads / 2 - per_stage;
+        const int64_t cap = (1536 - P.k - P.TB) / P.hop - per_stage - 1;   // keep the ring <= 1536 blocks
+        if (flush > cap) flush = cap;
+        if (flush < 1) flush = 1;
+        P.flush = static_cast<int32_t>(flush);
+        P.RB = static_cast<int32_t>((flush + per_stage + 1) * P.hop + P.k + P.TB + 1);
+    }
+    P.NS = 2;
     constexpr int A = 16 / sizeof(InT);
     P.stage_elems = ((P.TB * P.g + 1 + (A - 1) + A - 1) / A) * A + A;
     P.use_tma = (reinterpret_cast<uintptr_t>(x) % 16 == 0) ? 1 : 0;
 
-    size_t smem = 128 + static_cast<size_t>(P.NS) * P.stage_elems * sizeof(InT) + 16;
-    if (P.cpb > 1) smem += sizeof(double) * NQ * P.TB * P.cpb;
-    smem += sizeof(double) * NQ * P.RB;
-    if (P.k > kDirectK) smem += sizeof(double) * kNAdd * (P.RB + 1);
+    size_t smem = 128 + static_cast<size_t>(P.NS) * P.stage_elems * sizeof(InT);
+    if (P.cpb > 1) smem += partial_bytes(sizeof(InT), m4, td, P.TB * P.cpb);
+    smem += partial_bytes(sizeof(InT), m4, td, P.RB);
+    if (P.k > kDirectK) smem += sizeof(double) * kNPre * (P.RB + 1);
+    smem += 64;
     MHB_REQUIRE(smem <= 220 * 1024, MHB_E_UNSUPPORTED, "window_stats: geometry needs %zu bytes of shared memory", smem);
 
     // chunking: enough CTAs to fill the machine several times, each long enough to amortise the
     // pipeline fill and the (k - hop) halo blocks, short enough to keep the pivot local
     const int64_t win_per_stage = P.TB / P.hop > 0 ? P.TB / P.hop : 1;
     const int64_t total_windows = nw * geom->n_series;
-    const int64_t target_ctas = static_cast<int64_t>(kNumSMs) * 8;
+    const int64_t target_ctas = static_cast<int64_t>(kNumSMs) * 12;
     int64_t wpc = (total_windows + target_ctas - 1) / target_ctas;
     if (wpc < 8 * win_per_stage) wpc = 8 * win_per_stage;
     if (wpc > 64 * win_per_stage) wpc = 64 * win_per_stage;
