@@ -133,6 +133,14 @@ int32_t mhb_window_spectral_f32(const float* x, const mhb_windows* geom, double 
  * (FFTW_FORWARD, fft/_fft.py:8), +1 backward scaled by 1/n (fft/_fft.py:46-48). */
 int32_t mhb_fft_c128(const double* in, int32_t in_is_complex, int64_t n_rows, int32_t n,
                      int32_t direction, double* out, void* stream);
+/* The same reducers on caller-supplied PSD rows (float64 [n_rows][nb]) and frequency vector -- the
+ * literal signatures hrv.power_band(psd, freqs, lower, upper) (heart/hrv.py:173-179),
+ * relative_power_band (:192-198), density.peak_frequency (density.py:18-32) and
+ * information.entropy(x) (information.py:10-20; column MHB_S_ENTROPY, freqs may be NULL).
+ * h_params: (lo, hi) per column, NaN = None.  out = float64 [n_rows][n_features]. */
+int32_t mhb_psd_reduce_f64(const double* psd, const double* freqs, int64_t n_rows, int32_t nb,
+                           const int32_t* h_features, const double* h_params, int32_t n_features,
+                           double* out, void* stream);
 /* raw one-sided PSD rows, float32 in -> float64|float32 [n_series][nw][W/2+1] */
 int32_t mhb_window_psd_f32(const float* x, const mhb_windows* geom, void* psd_out, int32_t out_f32,
                            void* stream);

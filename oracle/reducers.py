@@ -113,8 +113,13 @@ def w_kurtosis_excess(w):
 
 @njit(cache=True)
 def w_coeff_var(w):
-    # stats.py:142-153: std / mean, no zero guard (inf / nan propagate)
-    return w_std(w) / w_mean(w)
+    # stats.py:142-153: std / mean, no zero guard.  mean == 0 raises ZeroDivisionError under numba's
+    # default error model; IEEE (inf / nan) is the defined behaviour here.
+    m = w_mean(w)
+    sd = w_std(w)
+    if m == 0:
+        return np.nan if sd == 0 else np.inf
+    return sd / m
 
 
 # --------------------------------------------------------------------------- order statistics
@@ -234,15 +239,25 @@ def w_hjorth_activity(w):
 
 @njit(cache=True)
 def w_hjorth_mobility(w):
-    # timedom.py:98-114: sqrt(var(gradient(x)) / var(x))
-    return np.sqrt(w_var(gradient(w)) / w_var(w))
+    # timedom.py:98-114: sqrt(var(gradient(x)) / var(x)).  A constant window divides 0 by 0: numba's
+    # default error model raises ZeroDivisionError there (and leaves garbage under prange); the defined
+    # behaviour both sides of the parity tests use is IEEE: nan.
+    vx = w_var(w)
+    v1 = w_var(gradient(w))
+    if vx == 0:
+        return np.nan if v1 == 0 else np.inf
+    return np.sqrt(v1 / vx)
 
 
 @njit(cache=True)
 def w_hjorth_complexity(w):
     # timedom.py:135-151: mobility(gradient(x)) / mobility(x)
     d1 = gradient(w)
-    return w_hjorth_mobility(d1) / np.sqrt(w_var(d1) / w_var(w))
+    m0 = w_hjorth_mobility(w)
+    m1 = w_hjorth_mobility(d1)
+    if m0 == 0 or np.isnan(m0) or np.isnan(m1):
+        return np.nan if (np.isnan(m0) or np.isnan(m1) or m1 == 0) else np.inf
+    return m1 / m0
 
 
 # --------------------------------------------------------------------------- information

@@ -58,6 +58,7 @@ SIGNATURES = {
                                          C.POINTER(MhbTable), _vp]),
     "mhb_window_spectral_f32": (C.c_int32, [_vp, C.POINTER(MhbWindows), C.c_double, _i32p, _f64p, C.c_int32,
                                             C.POINTER(MhbTable), _vp]),
+    "mhb_psd_reduce_f64": (C.c_int32, [_vp, _vp, C.c_int64, C.c_int32, _i32p, _f64p, C.c_int32, _vp, _vp]),
     "mhb_fft_c128": (C.c_int32, [_vp, C.c_int32, C.c_int64, C.c_int32, C.c_int32, _vp, _vp]),
     "mhb_window_psd_f32": (C.c_int32, [_vp, C.POINTER(MhbWindows), _vp, C.c_int32, _vp]),
     "mhb_haversine_elementwise": (C.c_int32, [_vp, _vp, _vp, _vp, C.c_int64, _vp, _vp]),

@@ -1,0 +1,167 @@
+// In-shared-memory mixed-radix Stockham FFT used by the spectral kernels (no cuFFT).
+//
+// The reference's FFT provider is FFTW through a 6-line CFFI shim, one plan per call
+// (src/mhealth/fft/_fftw_binder.py:8-20), or numpy's pocketfft; here a thread group (a warp or a
+// CTA) transforms one row that lives in shared memory: radix 4 / 2 / 3 / 5 butterflies plus a
+// generic O(p^2) butterfly for other primes <= 31, autosort (no bit reversal), twiddles from a
+// shared table that the CTA fills once with sincospi in float64.
+#pragma once
+#include "common.cuh"
+
+namespace mhb {
+
+constexpr int kMaxRadices = 24;
+constexpr int kMaxPrime = 31;
+
+struct FftPlan {
+    int32_t n;                    // transform length
+    int32_t n_radices;
+    int32_t radix[kMaxRadices];
+};
+
+// host: factor n into supported radices; false if a prime factor > kMaxPrime remains
+static inline bool fft_plan(int32_t n, FftPlan* p) {
+    p->n = n;
+    p->n_radices = 0;
+    int32_t r = n;
+    auto push = [&](int f) { p->radix[p->n_radices++] = f; };
+    while (r % 4 == 0) { push(4); r /= 4; }
+    while (r % 2 == 0) { push(2); r /= 2; }
+    for (int f = 3; f <= kMaxPrime; f += 2)
+        while (r % f == 0) {
+            if (p->n_radices >= kMaxRadices) return false;
+            push(f);
+            r /= f;
+        }
+    return r == 1;
+}
+
+template <typename T>
+struct Cx {
+    T x, y;
+};
+template <typename T>
+__device__ __forceinline__ Cx<T> cadd(Cx<T> a, Cx<T> b) { return {a.x + b.x, a.y + b.y}; }
+template <typename T>
+__device__ __forceinline__ Cx<T> csub(Cx<T> a, Cx<T> b) { return {a.x - b.x, a.y - b.y}; }
+template <typename T>
+__device__ __forceinline__ Cx<T> cmul(Cx<T> a, Cx<T> b) { return {a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x}; }
+template <typename T>
+__device__ __forceinline__ Cx<T> cscale(Cx<T> a, T s) { return {a.x * s, a.y * s}; }
+template <typename T>
+__device__ __forceinline__ Cx<T> mul_neg_i(Cx<T> a) { return {a.y, -a.x}; }   // a * (-i)
+
+// fill tw[j] = exp(-2 pi i j / n), j = 0..count-1, cooperatively by `nthreads` threads
+template <typename T>
+__device__ __forceinline__ void fill_twiddles(Cx<T>* tw, int n, int count, int rank, int nthreads) {
+    for (int j = rank; j < count; j += nthreads) {
+        double s, c;
+        sincospi(-2.0 * static_cast<double>(j) / static_cast<double>(n), &s, &c);
+        tw[j] = {static_cast<T>(c), static_cast<T>(s)};
+    }
+}
+
+// One Stockham pass of radix R: `in` -> `out`, both n complex values in shared memory.
+// ns = product of the radices already applied.  Executed by G threads with rank r.
+template <typename T, int R>
+__device__ __forceinline__ void stockham_pass(const Cx<T>* __restrict__ in, Cx<T>* __restrict__ out, int n, int ns,
+                                              const Cx<T>* __restrict__ tw, int r, int G) {
+    const int nb = n / R;                 // butterflies
+    const int tstep = n / (ns * R);       // twiddle table stride for angle 2 pi k / (ns R)
+    for (int j = r; j < nb; j += G) {
+        const int k = j % ns;
+        Cx<T> a[R];
+#pragma unroll
+        for (int t = 0; t < R; ++t) a[t] = in[j + t * nb];
+        if (ns > 1) {
+#pragma unroll
+            for (int t = 1; t < R; ++t) a[t] = cmul(a[t], tw[t * k * tstep]);
+        }
+        Cx<T> y[R];
+        if (R == 2) {
+            y[0] = cadd(a[0], a[1]);
+            y[1] = csub(a[0], a[1]);
+        } else if (R == 3) {
+            const T s = static_cast<T>(0.86602540378443864676);
+            const Cx<T> t1 = cadd(a[1], a[2]);
+            const Cx<T> t2 = {a[0].x - t1.x * static_cast<T>(0.5), a[0].y - t1.y * static_cast<T>(0.5)};
+            const Cx<T> t3 = cscale(csub(a[1], a[2]), s);
+            y[0] = cadd(a[0], t1);
+            y[1] = {t2.x + t3.y, t2.y - t3.x};
+            y[2] = {t2.x - t3.y, t2.y + t3.x};
+        } else if (R == 4) {
+            const Cx<T> t0 = cadd(a[0], a[2]), t1 = csub(a[0], a[2]);
+            const Cx<T> t2 = cadd(a[1], a[3]), t3 = mul_neg_i(csub(a[1], a[3]));
+            y[0] = cadd(t0, t2);
+            y[2] = csub(t0, t2);
+            y[1] = cadd(t1, t3);
+            y[3] = csub(t1, t3);
+        } else if (R == 5) {
+            const T c1 = static_cast<T>(0.30901699437494742410), c2 = static_cast<T>(-0.80901699437494742410);
+            const T s1 = static_cast<T>(0.95105651629515357212), s2 = static_cast<T>(0.58778525229247312917);
+            const Cx<T> p1 = cadd(a[1], a[4]), m1 = csub(a[1], a[4]);
+            const Cx<T> p2 = cadd(a[2], a[3]), m2 = csub(a[2], a[3]);
+            y[0] = {a[0].x + p1.x + p2.x, a[0].y + p1.y + p2.y};
+            const Cx<T> u1 = {a[0].x + c1 * p1.x + c2 * p2.x, a[0].y + c1 * p1.y + c2 * p2.y};
+            const Cx<T> u2 = {a[0].x + c2 * p1.x + c1 * p2.x, a[0].y + c2 * p1.y + c1 * p2.y};
+            const Cx<T> v1 = mul_neg_i(Cx<T>{s1 * m1.x + s2 * m2.x, s1 * m1.y + s2 * m2.y});
+            const Cx<T> v2 = mul_neg_i(Cx<T>{s2 * m1.x - s1 * m2.x, s2 * m1.y - s1 * m2.y});
+            y[1] = cadd(u1, v1);
+            y[4] = csub(u1, v1);
+            y[2] = cadd(u2, v2);
+            y[3] = csub(u2, v2);
+        }
+        const int o = (j - k) * R + k;
+#pragma unroll
+        for (int t = 0; t < R; ++t) out[o + t * ns] = y[t];
+    }
+}
+
+// generic prime radix p (7..31): O(p^2) butterfly, DFT matrix entries from the twiddle table
+template <typename T>
+__device__ __forceinline__ void stockham_pass_generic(const Cx<T>* __restrict__ in, Cx<T>* __restrict__ out, int n,
+                                                      int ns, int p, const Cx<T>* __restrict__ tw, int r, int G) {
+    const int nb = n / p;
+    const int tstep = n / (ns * p);
+    const int pstep = n / p;              // exp(-2 pi i u / p) = tw[u * pstep]
+    for (int j = r; j < nb; j += G) {
+        const int k = j % ns;
+        const int o = (j - k) * p + k;
+        for (int t = 0; t < p; ++t) {
+            Cx<T> acc = in[j];
+            for (int u = 1; u < p; ++u) {
+                Cx<T> a = in[j + u * nb];
+                if (ns > 1) a = cmul(a, tw[u * k * tstep]);
+                acc = cadd(acc, cmul(a, tw[((t * u) % p) * pstep]));
+            }
+            out[o + t * ns] = acc;
+        }
+    }
+}
+
+// Full transform.  Returns the buffer that holds the result (a or b).  sync() separates passes.
+template <typename T, typename SyncFn>
+__device__ __forceinline__ Cx<T>* stockham_fft(Cx<T>* a, Cx<T>* b, const FftPlan& plan, const Cx<T>* tw, int r, int G,
+                                               SyncFn sync) {
+    int ns = 1;
+    Cx<T>* in = a;
+    Cx<T>* out = b;
+    for (int i = 0; i < plan.n_radices; ++i) {
+        const int R = plan.radix[i];
+        switch (R) {
+            case 2: stockham_pass<T, 2>(in, out, plan.n, ns, tw, r, G); break;
+            case 3: stockham_pass<T, 3>(in, out, plan.n, ns, tw, r, G); break;
+            case 4: stockham_pass<T, 4>(in, out, plan.n, ns, tw, r, G); break;
+            case 5: stockham_pass<T, 5>(in, out, plan.n, ns, tw, r, G); break;
+            default: stockham_pass_generic<T>(in, out, plan.n, ns, R, tw, r, G); break;
+        }
+        ns *= R;
+        sync();
+        Cx<T>* t = in;
+        in = out;
+        out = t;
+    }
+    return in;
+}
+
+}  // namespace mhb

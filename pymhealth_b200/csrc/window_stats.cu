@@ -609,10 +609,6 @@ int32_t window_stats_impl(const InT* x, const mhb_windows* geom, const int32_t* 
                 MHB_E_ARG, "window_stats: bad series geometry");
     MHB_REQUIRE(n_features >= 0 && n_features <= kMaxFeat, MHB_E_ARG, "window_stats: 0..%d features per call", kMaxFeat);
     MHB_REQUIRE(n_features == 0 || h_features, MHB_E_ARG, "window_stats: null feature list");
-    const int64_t nw = n_windows_host(geom->series_len, geom->wsize, geom->wstep);
-    if (nw == 0 || geom->n_series == 0 || n_features == 0) return MHB_OK;
-    MHB_REQUIRE(x && table->out, MHB_E_ARG, "window_stats: null data/output pointer");
-
     StatsPlan P;
     memset(&P, 0, sizeof(P));
     bool m4 = false, td = false;
@@ -624,6 +620,9 @@ int32_t window_stats_impl(const InT* x, const mhb_windows* geom, const int32_t* 
         if (f == MHB_F_ZERO_CROSSINGS || f == MHB_F_LINE_LENGTH) td = true;
         P.feat[j] = f;
     }
+    const int64_t nw = n_windows_host(geom->series_len, geom->wsize, geom->wstep);
+    if (nw == 0 || geom->n_series == 0 || n_features == 0) return MHB_OK;
+    MHB_REQUIRE(x && table->out, MHB_E_ARG, "window_stats: null data/output pointer");
     P.n_features = n_features;
     P.x = x;
     P.series_len = geom->series_len;
@@ -631,7 +630,7 @@ int32_t window_stats_impl(const InT* x, const mhb_windows* geom, const int32_t* 
     P.total_elems = (geom->n_series - 1) * geom->series_stride + geom->series_len;
     P.nw = nw;
     P.W = geom->wsize;
-    P.S = geom->wstep;
+    P.S = nw == 1 ? geom->wsize : geom->wstep;      // a single window: the hop is irrelevant, keep g = W
     P.th = zc_threshold;
     P.inv_n = 1.0 / static_cast<double>(geom->wsize);
     P.out = table->out;

@@ -14,9 +14,10 @@ from . import _lib as L
 
 class Feature:
     """One output column: family 'stream' | 'order' | 'spectral', C-ABI feature id, parameters."""
-    __slots__ = ("family", "fid", "params", "name")
+    __slots__ = ("family", "fid", "params", "name", "fs")
 
     def __init__(self, family, fid, params=(), name=None):
+        self.fs = None
         self.family = family
         self.fid = int(fid)
         self.params = tuple(float(p) if p is not None else math.nan for p in params)

@@ -90,6 +90,12 @@ def resolve(func):
             if len(func.keywords) != 1:
                 raise NotImplementedError("partial with several keywords is not a supported reducer: %r" % (func,))
             params = tuple(func.keywords.values())
+    from .spectral import SpectralReducer
+    from .generic import stats as _stats      # noqa: F401  (registers the numpy aliases)
+    if isinstance(base, SpectralReducer):
+        if params:
+            raise NotImplementedError("spectral reducers carry their parameters; do not wrap them in partial()")
+        return base.feature(), base.integer
     red = None
     if isinstance(base, Reducer):
         red = base

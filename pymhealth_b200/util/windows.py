@@ -54,7 +54,13 @@ def _apply(features, arr, wsize, wstep):
         wsize, wstep = int(wsize) * k, int(wstep) * k
     elif a.ndim != 1:
         raise ValueError("rolling_apply takes 1-D (or 2-D, axis-0 windows) arrays")
-    tab = window_table(a, int(wsize), int(wstep), features, zc_threshold=_zc_threshold(features))
+    fss = {f.fs for f in features if f.family == "spectral"}
+    if len(fss) > 1:
+        raise NotImplementedError("one sampling rate per rolling_apply call")
+    if fss and a.dtype != np.float32:
+        a = a.astype(np.float32)        # the spectral kernel computes in float32 (float64 sums)
+    tab = window_table(a, int(wsize), int(wstep), features, zc_threshold=_zc_threshold(features),
+                       fs=fss.pop() if fss else 1.0)
     return tab          # float64 [nw, n_features]  (windows.py:89: always float64)
 
 

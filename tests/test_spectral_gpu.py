@@ -1,0 +1,114 @@
+"""Kernel 2 (window FFT + PSD reducers, batched DFT) vs fixtures and the oracle.
+
+Tolerances.  The window FFT computes in float32 with float64 sums: a spectral column c of a window is
+accepted when |c - ref| <= 1e-5 * max(|ref|, total_power_of_that_window * 1e-3) for powers (a band
+that holds < 0.1 % of the window's power is judged against that floor), 1e-5 relative for entropy,
+and exactly for peak bins unless the reference's own two largest candidates are within 1e-5
+(a tie no float32 pipeline can order)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _check_power(got, want, total, what):
+    tol = 1e-5 * np.maximum(np.abs(want), 1e-3 * total)
+    bad = np.abs(got - want) > tol
+    assert not bad.any(), "%s: %d/%d off, worst rel %g" % (what, bad.sum(), bad.size,
+                                                           np.max(np.abs(got - want) / np.maximum(np.abs(want), 1e-300)))
+
+
+def _check_peaks(got_bin, psd_ref, lidx, uidx, what):
+    want = lidx + np.argmax(psd_ref[:, lidx:uidx], axis=1)
+    for i in np.nonzero(got_bin != want)[0]:
+        a, b = psd_ref[i, int(got_bin[i])], psd_ref[i, want[i]]
+        assert abs(a - b) <= 1e-5 * b, "%s: window %d picked bin %d (%.6g) over %d (%.6g)" % (
+            what, i, got_bin[i], a, want[i], b)
+
+
+@pytest.mark.parametrize("case", ["acc", "ppg", "odd"])
+def test_golden_spectral(ref_spectral, case):
+    from pymhealth_b200 import spectral as SP
+    from pymhealth_b200.util import rolling_apply
+    from oracle import spectral as OS
+    x = ref_spectral[case + "/x"]
+    W, S, fs = ref_spectral[case + "/wsf"]
+    W, S = int(W), int(S)
+    bands = [tuple(b) for b in ref_spectral[case + "/bands"]]
+    funcs = {"total": SP.total_power(fs), "entropy": SP.spectral_entropy(fs), "peak": SP.peak_frequency(fs, 0.3, 12.0),
+             "peak_bin": SP.peak_bin(fs, 0.3, 12.0), "peak_all": SP.peak_frequency(fs)}
+    for j, (lo, hi) in enumerate(bands):
+        funcs["bp%d" % j] = SP.band_power(fs, lo, hi)
+        funcs["rbp%d" % j] = SP.relative_band_power(fs, lo, hi)
+    got = rolling_apply(funcs)(x, W, S)
+    tot = ref_spectral[case + "/total_power"]
+    _check_power(got["total"], tot, tot, "total")
+    for j in range(len(bands)):
+        _check_power(got["bp%d" % j], ref_spectral[case + "/band_power"][:, j], tot, "band %d" % j)
+        _check_power(got["rbp%d" % j], ref_spectral[case + "/rel_band_power"][:, j], np.ones_like(tot), "rel band %d" % j)
+    np.testing.assert_allclose(got["entropy"], ref_spectral[case + "/entropy"], rtol=1e-5)
+    psd_ref, freqs = OS.window_psd(x, W, S, fs)
+    lidx, uidx = OS.first_index(freqs, 0.3), OS.first_index(freqs, 12.0)
+    _check_peaks(got["peak_bin"].astype(np.int64), psd_ref, lidx, uidx, "peak bin")
+    same = got["peak"] == ref_spectral[case + "/peak_frequency_0.3_12"]
+    assert same.mean() > 0.9
+    np.testing.assert_array_equal(got["peak"], freqs[got["peak_bin"].astype(np.int64)])
+    _check_peaks(np.round(got["peak_all"] / freqs[1]).astype(np.int64), psd_ref, 0, len(freqs), "peak all")
+    # raw PSD rows
+    psd, fr = SP.window_psd(x, W, S, fs)
+    np.testing.assert_array_equal(fr, freqs)
+    assert psd.shape == psd_ref.shape
+    err = np.abs(psd - psd_ref).max(axis=1)
+    assert np.all(err <= 1e-5 * psd_ref.max(axis=1))
+
+
+def test_fft_dropin(ref_spectral):
+    from pymhealth_b200 import fft as F
+    for case in ("acc", "ppg", "odd"):
+        x = ref_spectral[case + "/x"]
+        W = int(ref_spectral[case + "/wsf"][0])
+        spec = F.fft(x[:W].astype(np.float64))
+        want = ref_spectral[case + "/fft0"]
+        assert spec.dtype == np.complex128
+        np.testing.assert_allclose(spec, want, rtol=0, atol=1e-12 * np.abs(want).max())
+        back = F.ifft(want)
+        np.testing.assert_allclose(back, ref_spectral[case + "/ifft0"], rtol=0, atol=1e-13 * np.abs(x[:W]).max() + 1e-15)
+    rng = np.random.default_rng(0)
+    for n in (1, 2, 3, 7, 31, 60, 250, 500, 961, 1000, 1920, 2 * 3 * 5 * 7 * 11):
+        a = rng.standard_normal((3, n)) + 1j * rng.standard_normal((3, n))
+        np.testing.assert_allclose(F.fft(a), np.fft.fft(a, axis=1), rtol=0, atol=1e-12 * n)
+        np.testing.assert_allclose(F.ifft(F.fft(a)), a, rtol=0, atol=1e-13 * n)           # round trip
+    with pytest.raises(NotImplementedError):
+        F.fft(np.zeros(37 * 4))
+
+
+def test_psd_reducers_literal_signatures(ref_spectral):
+    from pymhealth_b200.heart import hrv
+    from pymhealth_b200.generic.frequency import density
+    from pymhealth_b200.generic import information
+    from oracle import spectral as OS
+    x = ref_spectral["acc/x"]
+    psd, freqs = OS.window_psd(x, 500, 250, 50.0)
+    for i in (0, 7, psd.shape[0] - 1):
+        assert hrv.power_band(psd[i], freqs, 0.5, 3.0) == pytest.approx(ref_spectral["acc/band_power"][i, 0], rel=1e-13)
+        assert hrv.relative_power_band(psd[i], freqs, 3.0, 8.0) == pytest.approx(ref_spectral["acc/rel_band_power"][i, 1], rel=1e-13)
+        assert hrv.power_band(psd[i], freqs) == pytest.approx(ref_spectral["acc/total_power"][i], rel=1e-13)
+        assert density.peak_frequency(psd[i], freqs, 0.3, 12.0) == ref_spectral["acc/peak_frequency_0.3_12"][i]
+        assert density.peak_frequency(psd[i], freqs) == ref_spectral["acc/peak_frequency_all"][i]
+        assert information.entropy(psd[i]) == pytest.approx(ref_spectral["acc/entropy"][i], rel=1e-12)
+    assert density.first_index(freqs, 0.3) == OS.first_index(freqs, 0.3)
+
+
+def test_linearity_and_parseval_full_config2():
+    """Config-2 size properties: Parseval (sum of the two-sided PSD = W * sum x^2) and scaling."""
+    import torch
+    from pymhealth_b200 import synth, engine, spectral as SP
+    x = torch.from_numpy(synth.accelerometer(1, 1_000_000)).cuda()
+    W, S = 500, 250
+    psd, _ = SP.window_psd(x, W, S, 50.0, out_dtype=torch.float64)
+    two_sided = psd[..., 0] + 2 * psd[..., 1:-1].sum(-1) + psd[..., -1]
+    win = x.double().unfold(1, W, S)
+    torch.testing.assert_close(two_sided, W * (win * win).sum(-1), rtol=2e-6, atol=0)
+    psd2, _ = SP.window_psd(x * 3.0, W, S, 50.0, out_dtype=torch.float64)
+    err = (psd2 - psd * 9.0).abs().amax(dim=-1)
+    assert bool((err <= 1e-5 * 9.0 * psd.amax(dim=-1)).all())      # float32 FFT: error scales with the row's peak
