@@ -1,0 +1,373 @@
+#!/usr/bin/env python3
+"""Benchmark of the window-feature hot path (BASELINE.json: "feature windows/sec at 1/2/4/8 B200 +
+HBM GB/s fraction vs numba host").
+
+Workload = BASELINE.json configs[2] (1,000 subjects x 7 days triaxial accelerometer at 50 Hz, 10 s
+windows with 50 % overlap, sharded by subject), weak scaling: every GPU holds 125 subjects (45.4 GB of
+float32 samples resident in HBM), so 8 GPUs process exactly the 1,000-subject configuration and N GPUs
+process 125 N subjects.  A step is one pass of the hot path over the rank's shard: kernel 1a (10
+statistical / time-domain columns) + kernel 2 (FFT + 6 spectral columns) -> one [windows, 16] float32
+feature table.  No collective is on the data path (subjects are independent); the only NCCL traffic is the
+gather of a per-subject summary table after the timed region.
+
+    python bench.py --gpus 1 --steps 10 --warmup 3
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port P bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference ...      # the oracle port of the reference's CPU path, host cores
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np
+
+WSIZE, WSTEP, FS = 500, 250, 50.0
+WEEK = 30_240_000                     # 7 d x 86400 s x 50 Hz
+BANDS = [(0.5, 3.0), (3.0, 8.0)]
+PEAK = (0.3, 12.0)
+STREAM_NAMES = ["mean", "std", "var", "min", "max", "drange", "skewness", "kurtosis", "zero_crossing_count",
+                "line_length"]
+SPECTRAL_NAMES = ["total_power", "band_power_0", "band_power_1", "rel_band_power_0", "peak_frequency",
+                  "spectral_entropy"]
+METRIC = "feature windows/sec"
+UNIT = "windows/s"
+
+
+def feature_list():
+    from pymhealth_b200 import spectral as SP
+    from pymhealth_b200.generic import stats, timedom
+    stream = [stats.mean.feature(), stats.std.feature(), stats.var.feature(), stats.dmin.feature(),
+              stats.dmax.feature(), stats.drange.feature(), stats.skewness.feature(), stats.kurtosis.feature(),
+              timedom.zero_crossing_count.feature(0.0), timedom.line_length.feature()]
+    spec = [SP.total_power(FS).feature(), SP.band_power(FS, *BANDS[0]).feature(), SP.band_power(FS, *BANDS[1]).feature(),
+            SP.relative_band_power(FS, *BANDS[0]).feature(), SP.peak_frequency(FS, *PEAK).feature(),
+            SP.spectral_entropy(FS).feature()]
+    return stream, spec
+
+
+def measured_peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------------------
+def oracle_features(x, want_table=False):
+    """The reference's CPU path (oracle port) for the 16 bench columns on x = [n_series, len] float32:
+    one rolling pass per statistical reducer (as rolling_apply's list form does, windows.py:98-107), numpy FFT over
+    the strided window view + PSD reducers.  Returns (seconds, n_windows[, table])."""
+    from oracle import windows as OW, spectral as OS
+    t0 = time.perf_counter()
+    cols = []
+    nwin = 0
+    for s in range(x.shape[0]):
+        xs = x[s]
+        per = [OW.rolling(n, xs, WSIZE, WSTEP, 0.0 if n == "zero_crossing_count" else None) for n in STREAM_NAMES]
+        tab = OS.spectral_table(xs, WSIZE, WSTEP, FS, BANDS, PEAK[0], PEAK[1])
+        per += [tab[k] for k in SPECTRAL_NAMES]
+        nwin += len(per[0])
+        if want_table:
+            cols.append(np.stack(per, axis=1))
+    dt = time.perf_counter() - t0
+    if want_table:
+        return dt, nwin, np.stack(cols)
+    return dt, nwin
+
+
+def warm_oracle():
+    """JIT-compile the numba drivers on a tiny input (excluded from every timing)."""
+    x = np.random.default_rng(0).standard_normal((1, 4 * WSIZE)).astype(np.float32)
+    oracle_features(x)
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    import numba
+    from pymhealth_b200 import synth
+    cores = numba.get_num_threads()
+    n = 4_320_000                                         # one subject-day per step, 3 axes
+    x = synth.accelerometer(0, n)
+    warm_oracle()
+    for _ in range(max(1, min(args.warmup, 2))):          # warm caches / thread pool; bounded
+        oracle_features(x)
+    total, wins = 0.0, 0
+    for _ in range(args.steps):
+        dt, nw = oracle_features(x)
+        total += dt
+        wins += nw
+    value = wins / total
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "config 3 (accelerometer 50 Hz, W=500 S=250, 16 feature columns); bounded sample per step: "
+                               "1 subject-day x 3 axes (51,837 axis-windows)", "wsize": WSIZE, "wstep": WSTEP,
+                   "features": STREAM_NAMES + SPECTRAL_NAMES},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": "1 subject-day x 3 axes per step, %d steps; oracle port of the reference's numba path "
+                                   "(the reference is pure Python + numba; /root/reference does not travel to the GPU box)" % args.steps},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.FIELDS,
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+
+    def stop(self, t0=None, t1=None):
+        """Summarise the samples taken between wall-clock t0 and t1 (the timed region)."""
+        import datetime
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill()
+            out = ""
+        sm, smax, power, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        rows = []
+        for ln in out.strip().splitlines():
+            parts = [p.strip() for p in ln.split(",")]
+            if len(parts) < 8:
+                continue
+            try:
+                ts = datetime.datetime.strptime(parts[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                rows.append((ts, float(parts[1]), float(parts[2]), float(parts[3]), parts[4:8]))
+            except ValueError:
+                continue
+        inside = [r for r in rows if t0 is not None and t0 <= r[0] <= t1]
+        if not inside and rows:          # region shorter than the sampling period: nearest samples under load
+            pmax = max(r[3] for r in rows)
+            inside = [r for r in rows if r[3] >= 0.8 * pmax]
+        for ts, a, b, c, flags in inside:
+            sm.append(a)
+            smax.append(b)
+            power.append(c)
+            for nme, v in zip(names, flags):
+                if v.lower().startswith("active"):
+                    reasons.add(nme)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(smax), "power_w_max": max(power),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def run_b200_arm(args):
+    import torch
+    import torch.distributed as dist
+    from pymhealth_b200 import engine, synth, sharded, _lib
+    from pymhealth_b200.pipeline import FeaturePipeline
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device; there is no CPU fallback (use --impl reference for the CPU arm)")
+    _lib.load()
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    if args.gpus != world and rank == 0:
+        print("note: --gpus %d but WORLD_SIZE=%d; reporting n_gpus=%d" % (args.gpus, world, world), file=sys.stderr)
+
+    nsub = args.subjects_per_gpu
+    n = args.samples
+    first = rank * nsub
+    stream_f, spec_f = feature_list()
+    feats = stream_f + spec_f
+    nf = len(feats)
+    nw = engine.n_windows(n, WSIZE, WSTEP)
+    x = synth.device_accelerometer(nsub, n, dev, first_subject=first).view(nsub * 3, n)
+    table = torch.empty((nsub * 3, nw, nf), dtype=torch.float32, device=dev)
+    t_stats = table[:, :, :len(stream_f)]
+    t_spec = table[:, :, len(stream_f):]
+    windows_per_step = nsub * 3 * nw
+
+    def step(evs=None):
+        if evs:
+            evs[0].record()
+        engine.window_table(x, WSIZE, WSTEP, stream_f, out=t_stats)
+        if evs:
+            evs[1].record()
+        engine.window_table(x, WSIZE, WSTEP, spec_f, fs=FS, out=t_spec)
+        if evs:
+            evs[2].record()
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    wall0 = time.time()
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
+    for k in range(args.steps):
+        step(evs[k])
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    wall1 = time.time()
+    clocks = sampler.stop(wall0, wall1) if rank == 0 else None
+    total_ms = evs[0][0].elapsed_time(evs[-1][2])
+    ms_stats = sum(e[0].elapsed_time(e[1]) for e in evs) / args.steps
+    ms_spec = sum(e[1].elapsed_time(e[2]) for e in evs) / args.steps
+    tmax = torch.tensor([total_ms, ms_stats, ms_spec], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    total_ms, ms_stats, ms_spec = (float(v) for v in tmax.cpu())
+    value = world * windows_per_step * args.steps / (total_ms * 1e-3)
+
+    # ---- end-to-end through the public host-buffer API (pinned host inputs, H2D + kernels + D2H per step)
+    e2e_sub = min(args.e2e_subjects, nsub)
+    hx = torch.empty((e2e_sub * 3, n), dtype=torch.float32).pin_memory()
+    hx.copy_(x[:e2e_sub * 3])
+    hout = torch.empty((e2e_sub * 3, nw, nf), dtype=torch.float32).pin_memory()
+    pipe = FeaturePipeline(feats, WSIZE, WSTEP, fs=FS, chunk_series=3)
+    pipe.run(hx, hout)
+    torch.cuda.synchronize()
+    check_ok = bool(torch.allclose(hout, table[:e2e_sub * 3].cpu(), rtol=1e-5, atol=1e-6, equal_nan=True))   # same kernels
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2e_steps = 3
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(e2e_steps):
+        pipe.run(hx, hout)
+    e1.record()
+    torch.cuda.synchronize()
+    e2e_ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
+    e2e_value = world * e2e_sub * 3 * nw * e2e_steps / (float(e2e_ms.cpu()) * 1e-3)
+
+    # ---- the one collective of the design: gather per-subject summary rows (mean of every column over the week)
+    summary = table.view(nsub, 3 * nw, nf).mean(dim=1)
+    gather_ms = 0.0
+    if world > 1:
+        torch.cuda.synchronize()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        full = sharded.gather_tables(summary, nsub * world)
+        g1.record()
+        torch.cuda.synchronize()
+        gather_ms = g0.elapsed_time(g1)
+        assert tuple(full.shape) == (nsub * world, nf)
+
+    if rank == 0:
+        peak, peak_src = measured_peak_gbs()
+        samples_b = nsub * 3 * n * 4
+
+        def roof(name, ms, ncols):
+            alg = samples_b + windows_per_step * ncols * 4
+            ach = alg / (ms * 1e-3) / 1e9
+            return {"kernel": name, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                    "traffic": None, "ms_per_launch": ms, "algorithmic_bytes": alg, "peak_source": peak_src}
+        k_stats = roof("window_stats_kernel (kernel 1a)", ms_stats, len(stream_f))
+        k_spec = roof("window_spectral_kernel (kernel 2)", ms_spec, len(spec_f))
+        dominant = k_spec if ms_spec >= ms_stats else k_stats
+        dominant = dict(dominant)
+        if dominant is not None and dominant["kernel"].startswith("window_spectral"):
+            dominant["note"] = ("kernel 2 is FP32-issue-bound (a 250-point complex FFT per 1,000 B window), not HBM-bound; "
+                                "frac is its HBM fraction all the same.  kernel 1a (HBM-bound) is listed under 'kernels'.")
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32 samples, f64 accumulation (stats) / f32 FFT with f64 sums (spectral)", "data": "synthetic",
+            "config": {"workload": "BASELINE configs[2]: 1,000 subjects x 7 d x 3 axes @ 50 Hz, W=500 S=250, sharded by subject; "
+                                   "%d subjects per GPU resident in HBM (weak scaling; 8 GPUs = the full 1,000)" % nsub,
+                       "subjects_per_gpu": nsub, "samples_per_axis": n, "windows_per_step_per_gpu": windows_per_step,
+                       "feature_columns": nf, "features": STREAM_NAMES + SPECTRAL_NAMES, "wsize": WSIZE, "wstep": WSTEP,
+                       "l2": "inputs (%.1f GB per GPU) are far larger than the 126 MB L2; no flush needed" % (samples_b / 1e9),
+                       "parallelism": "subject-sharded x%d, no data-path collective" % world},
+            "roofline": dominant,
+            "kernels": {"window_stats": k_stats, "window_spectral": k_spec},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(hx.numel() * 4),
+                    "d2h_bytes_per_step": int(hout.numel() * 4), "subjects_per_step_per_gpu": e2e_sub,
+                    "ms_per_step": float(e2e_ms.cpu()) / e2e_steps, "matches_resident_run": check_ok,
+                    "api": "pymhealth_b200.pipeline.FeaturePipeline.run (pinned host in, pinned host out)"},
+            "gpu_launches": 2 * args.steps,
+            "clocks": clocks,
+            "gather_ms": gather_ms,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            import numba
+            sx = x[:3].cpu().numpy()                                   # 1 subject x 3 axes x 7 d
+            if args.cpu_sample_samples and args.cpu_sample_samples < n:
+                sx = np.ascontiguousarray(sx[:, :args.cpu_sample_samples])
+            warm_oracle()
+            dt, nwin, tab = oracle_features(sx, want_table=True)
+            got = table[:3, :tab.shape[1]].cpu().numpy().astype(np.float64)
+            scale = np.maximum(np.abs(tab), np.abs(tab).mean(axis=(0, 1), keepdims=True) * 1e-3)
+            line["cpu_baseline"] = {"value": nwin / dt, "unit": UNIT, "cores": numba.get_num_threads(), "kind": "port",
+                                    "seconds": dt,
+                                    "sample": "1 subject x 3 axes x %d samples (%d axis-windows), 16 columns, one rolling pass per "
+                                              "statistical reducer + numpy FFT; numba prange on all host threads" % (sx.shape[1], nwin),
+                                    "max_rel_dev_vs_gpu": float(np.max(np.abs(got - tab) / scale))}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--subjects-per-gpu", type=int, default=int(os.environ.get("MHB_BENCH_SUBJECTS", "125")))
+    ap.add_argument("--samples", type=int, default=WEEK)
+    ap.add_argument("--e2e-subjects", type=int, default=8)
+    ap.add_argument("--cpu-sample-samples", type=int, default=0, help="truncate the CPU-baseline sample (debug)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "b200":
+        args.warmup = 3                      # timing rule: at least 3 warm-up steps
+    if args.impl == "reference":
+        return run_reference_arm(args)
+    return run_b200_arm(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())
