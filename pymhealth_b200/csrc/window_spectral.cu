@@ -17,11 +17,16 @@
 // arrive as integer bin ranges computed on the host with numpy's rfftfreq arithmetic, so the masks
 // are bit-exact.
 #include <cmath>
+#include <cstdlib>
 #include <math_constants.h>
 
 #include "fft_core.cuh"
 
 namespace mhb {
+
+int32_t spectral_batched_try(const float* x, const mhb_windows* geom, int64_t nw, double bin_hz, const int32_t* cols,
+                             const int32_t* lo, const int32_t* hi, int32_t n_cols, void* out, int32_t out_f32,
+                             int64_t o_series, int64_t o_window, int64_t o_col, void* stream);
 
 namespace {
 
@@ -232,6 +237,12 @@ int32_t spectral_launch(const float* x, const mhb_windows* geom, double fs, cons
             P.lo[j] = 0;
             P.hi[j] = P.nb;
         }
+    }
+    if (n_features > 0 && getenv("MHB_SPECTRAL_GENERIC") == nullptr) {
+        // compile-time-planned batched kernel for the hot geometries (spectral_batched.cu)
+        const int32_t st = spectral_batched_try(x, geom, nw, P.bin_hz, P.col, P.lo, P.hi, n_features, out, out_f32,
+                                                o_series, o_window, o_col, stream_v);
+        if (st != -100) return st;
     }
     const size_t smem = sizeof(Cx<float>) * (static_cast<size_t>(P.N) + (P.even ? P.nb : 0) +
                                              static_cast<size_t>(kWarps) * 2 * P.N);

@@ -26,8 +26,11 @@ def _check_peaks(got_bin, psd_ref, lidx, uidx, what):
             what, i, got_bin[i], a, want[i], b)
 
 
-@pytest.mark.parametrize("case", ["acc", "ppg", "odd"])
-def test_golden_spectral(ref_spectral, case):
+@pytest.mark.parametrize("case", ["acc", "ppg", "odd", "acc-generic"])
+def test_golden_spectral(ref_spectral, case, monkeypatch):
+    if case.endswith("-generic"):           # W=500/S=250 normally takes the batched kernel: cover the generic one too
+        monkeypatch.setenv("MHB_SPECTRAL_GENERIC", "1")
+        case = case.split("-")[0]
     from pymhealth_b200 import spectral as SP
     from pymhealth_b200.util import rolling_apply
     from oracle import spectral as OS

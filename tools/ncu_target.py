@@ -24,9 +24,15 @@ def main():
         x = synth.device_ppg(32, 5_529_600, dev)
         W, S = 1920, 64
     feats = lvl0 if what.endswith("lvl0") else full
+    if what.endswith("spec"):
+        from pymhealth_b200 import spectral as SP
+        fs = 50.0 if what.startswith("c3") else 64.0
+        feats = [SP.total_power(fs).feature(), SP.band_power(fs, 0.5, 3.0).feature(), SP.band_power(fs, 3.0, 8.0).feature(),
+                 SP.relative_band_power(fs, 0.5, 3.0).feature(), SP.peak_frequency(fs, 0.3, 12.0).feature(),
+                 SP.spectral_entropy(fs).feature()]
     out = torch.empty((x.shape[0], engine.n_windows(x.shape[1], W, S), len(feats)), dtype=torch.float32, device=dev)
     for _ in range(iters):
-        engine.window_table(x, W, S, feats, out=out)
+        engine.window_table(x, W, S, feats, out=out, fs=50.0 if what.startswith("c3") else 64.0)
     torch.cuda.synchronize()
     print("ok", what, float(out[0, 0, 0]))
 
