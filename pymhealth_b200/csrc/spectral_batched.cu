@@ -442,7 +442,7 @@ __global__ void __launch_bounds__(kThreadsB, MINB) spectral_batched_kernel(const
                     if (arg == 0x7fffffff) v = CUDART_NAN;
                     else v = kind == MHB_S_PEAK_BIN ? static_cast<double>(arg) : static_cast<double>(arg) * P.bin_hz;
                 }
-                if (l16 == 0) res[j] = v;
+                if (act && l16 == 0) res[j] = v;      // idle half-warps alias window 0: they must not store
             }
             __syncwarp();
             if (act && l16 < P.n_cols) {                 // lane j stores column j: one coalesced row segment

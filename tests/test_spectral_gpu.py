@@ -65,6 +65,31 @@ def test_golden_spectral(ref_spectral, case, monkeypatch):
     assert np.all(err <= 1e-5 * psd_ref.max(axis=1))
 
 
+@pytest.mark.parametrize("n", [500, 749, 4250, 4251, 8137, 12500 + 250 * 16 * 3])
+def test_batched_kernel_ragged_batches(n):
+    """The W=500/S=250 fast path works on batches of 16 windows: cover short / ragged last batches, several series,
+    an unaligned base pointer and a row stride that defeats TMA, against the generic kernel and the oracle."""
+    import torch
+    from oracle import spectral as OS
+    from pymhealth_b200 import engine, synth, spectral as SP
+    x = np.stack([synth.accelerometer(40 + s, n)[s % 3] for s in range(5)])
+    feats = [SP.total_power(50.0).feature(), SP.band_power(50.0, 0.5, 3.0).feature(), SP.peak_bin(50.0, 0.3, 12.0).feature(),
+             SP.spectral_entropy(50.0).feature()]
+    xt = torch.from_numpy(x).cuda()
+    got = engine.window_table(xt, 500, 250, feats, fs=50.0, out_dtype=torch.float64).cpu().numpy()
+    wide = torch.zeros((5, n + 3), dtype=torch.float32, device="cuda")        # stride not a multiple of 4 -> no TMA
+    wide[:, :n] = xt
+    got2 = engine.window_table(wide[:, :n], 500, 250, feats, fs=50.0, out_dtype=torch.float64).cpu().numpy()
+    np.testing.assert_array_equal(got, got2)
+    for s in range(5):
+        tab = OS.spectral_table(x[s], 500, 250, 50.0, [(0.5, 3.0)], 0.3, 12.0)
+        _check_power(got[s, :, 0], tab["total_power"], tab["total_power"], "total")
+        _check_power(got[s, :, 1], tab["band_power_0"], tab["total_power"], "band")
+        np.testing.assert_allclose(got[s, :, 3], tab["spectral_entropy"], rtol=1e-5)
+        psd_ref, freqs = OS.window_psd(x[s], 500, 250, 50.0)
+        _check_peaks(got[s, :, 2].astype(np.int64), psd_ref, OS.first_index(freqs, 0.3), OS.first_index(freqs, 12.0), "peak")
+
+
 def test_fft_dropin(ref_spectral):
     from pymhealth_b200 import fft as F
     for case in ("acc", "ppg", "odd"):
