@@ -123,7 +123,7 @@ def run_reference_arm(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     return 0
 
 
@@ -343,14 +343,33 @@ def run_b200_arm(args):
                                     "sample": "1 subject x 3 axes x %d samples (%d axis-windows), 16 columns, one rolling pass per "
                                               "statistical reducer + numpy FFT; numba prange on all host threads" % (sx.shape[1], nwin),
                                     "max_rel_dev_vs_gpu": float(np.max(np.abs(got - tab) / scale))}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
     return 0
 
 
+def _claim_stdout():
+    """Keep fd 1 clean for the ONE JSON line: libraries (NCCL's version banner, numba warnings) that write to
+    stdout are sent to stderr; the JSON goes to the saved descriptor."""
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    return os.fdopen(saved, "w")
+
+
+JSON_OUT = None
+
+
+def emit(line):
+    JSON_OUT.write(json.dumps(line) + "\n")
+    JSON_OUT.flush()
+
+
 def main():
+    global JSON_OUT
+    JSON_OUT = _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
