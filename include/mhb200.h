@@ -119,6 +119,36 @@ int32_t mhb_window_order_f64(const double* x, const mhb_windows* geom,
                              const int32_t* h_features, const double* h_params, int32_t n_features,
                              const mhb_table* table, void* stream);
 
+/* ---- non-uniform (index-addressed) windows -----------------------------------------------------
+ * get_indices(index, wsize, wstep) (util/windows.py:162-178): starts = arange(index[0], index[-1], wstep),
+ * ends = starts + wsize, both located in ``index`` by a left searchsorted.  ``first`` = index[0];
+ * ``n_windows`` = len(arange(index[0], index[-1], wstep)) (host arithmetic).  out_indices = int64 [2][n_windows]
+ * (row 0 starts, row 1 ends).  _i64 serves integer / datetime64 / timedelta64 indices, _f64 float indices. */
+int32_t mhb_get_indices_i64(const int64_t* index, int64_t n, int64_t first, int64_t wsize, int64_t wstep,
+                            int64_t n_windows, int64_t* out_indices, void* stream);
+int32_t mhb_get_indices_f64(const double* index, int64_t n, double first, double wsize, double wstep,
+                            int64_t n_windows, int64_t* out_indices, void* stream);
+/* indices_rolling_apply(f, min_window_len)(indices, arr) (util/windows.py:122-159): row i of the table =
+ * reducers of x[starts[i] : ends[i]], NaN in every column when ends[i] - starts[i] < min_window_len (or the
+ * window is empty).  Streaming family (ids MHB_F_MEAN..MHB_F_SUM), one warp per window, warp-shuffle
+ * combination of float64 partial records.  table->series_stride is ignored (one series). */
+int32_t mhb_segment_stats_f32(const float* x, int64_t n, const int64_t* starts, const int64_t* ends,
+                              int64_t n_windows, int64_t min_window_len, const int32_t* h_features,
+                              int32_t n_features, double zc_threshold, const mhb_table* table, void* stream);
+int32_t mhb_segment_stats_f64(const double* x, int64_t n, const int64_t* starts, const int64_t* ends,
+                              int64_t n_windows, int64_t min_window_len, const int32_t* h_features,
+                              int32_t n_features, double zc_threshold, const mhb_table* table, void* stream);
+/* the order / derivative family (ids MHB_F_MEDIAN..MHB_F_HJORTH_COMPLEXITY) on the same windows;
+ * max_window_len = max(ends - starts) sizes the shared-memory sort buffer. */
+int32_t mhb_segment_order_f32(const float* x, int64_t n, const int64_t* starts, const int64_t* ends,
+                              int64_t n_windows, int64_t max_window_len, int64_t min_window_len,
+                              const int32_t* h_features, const double* h_params, int32_t n_features,
+                              const mhb_table* table, void* stream);
+int32_t mhb_segment_order_f64(const double* x, int64_t n, const int64_t* starts, const int64_t* ends,
+                              int64_t n_windows, int64_t max_window_len, int64_t min_window_len,
+                              const int32_t* h_features, const double* h_params, int32_t n_features,
+                              const mhb_table* table, void* stream);
+
 /* ---- kernel 2: per-window FFT + PSD reducers ---------------------------------------------
  * Replaces the user-composed chain view -> mhealth.fft.fft -> |F|^2 -> hrv.power_band /
  * density.peak_frequency / information.entropy.  One-sided PSD, bins 0..W/2,

@@ -56,6 +56,16 @@ SIGNATURES = {
                                          C.POINTER(MhbTable), _vp]),
     "mhb_window_order_f64": (C.c_int32, [_vp, C.POINTER(MhbWindows), _i32p, _f64p, C.c_int32,
                                          C.POINTER(MhbTable), _vp]),
+    "mhb_get_indices_i64": (C.c_int32, [_vp, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int64, _vp, _vp]),
+    "mhb_get_indices_f64": (C.c_int32, [_vp, C.c_int64, C.c_double, C.c_double, C.c_double, C.c_int64, _vp, _vp]),
+    "mhb_segment_stats_f32": (C.c_int32, [_vp, C.c_int64, _vp, _vp, C.c_int64, C.c_int64, _i32p, C.c_int32,
+                                          C.c_double, C.POINTER(MhbTable), _vp]),
+    "mhb_segment_stats_f64": (C.c_int32, [_vp, C.c_int64, _vp, _vp, C.c_int64, C.c_int64, _i32p, C.c_int32,
+                                          C.c_double, C.POINTER(MhbTable), _vp]),
+    "mhb_segment_order_f32": (C.c_int32, [_vp, C.c_int64, _vp, _vp, C.c_int64, C.c_int64, C.c_int64, _i32p, _f64p,
+                                          C.c_int32, C.POINTER(MhbTable), _vp]),
+    "mhb_segment_order_f64": (C.c_int32, [_vp, C.c_int64, _vp, _vp, C.c_int64, C.c_int64, C.c_int64, _i32p, _f64p,
+                                          C.c_int32, C.POINTER(MhbTable), _vp]),
     "mhb_window_spectral_f32": (C.c_int32, [_vp, C.POINTER(MhbWindows), C.c_double, _i32p, _f64p, C.c_int32,
                                             C.POINTER(MhbTable), _vp]),
     "mhb_psd_reduce_f64": (C.c_int32, [_vp, _vp, C.c_int64, C.c_int32, _i32p, _f64p, C.c_int32, _vp, _vp]),

@@ -33,6 +33,10 @@ struct OrderPlan {
     int32_t need_sort, need_hjorth;
     int32_t feat[kMaxFeat];
     double param[kMaxFeat];
+    // segment mode (non-uniform windows, util/windows.py:122-159): window w = x[starts[w] : ends[w]]
+    const int64_t* starts;
+    const int64_t* ends;
+    int64_t n_total, min_len;
 };
 
 template <typename T>
@@ -119,15 +123,36 @@ __global__ void __launch_bounds__(256) window_order_kernel(const OrderPlan P) {
     const int r = Group<G>::rank();
     InT* buf = reinterpret_cast<InT*>(smem_raw) + static_cast<size_t>(grp) * P.P2;
     const InT* xg = reinterpret_cast<const InT*>(P.x);
-    const int n = P.W;
+    int n = P.W;
+    const bool segmented = P.starts != nullptr;
 
     for (int64_t w = static_cast<int64_t>(blockIdx.x) * groups_per_cta + grp; w < P.total_windows;
          w += static_cast<int64_t>(gridDim.x) * groups_per_cta) {
-        const int64_t series = w / P.nw;
-        const int64_t wi = w - series * P.nw;
+        int64_t series = w / P.nw;
+        int64_t wi = w - series * P.nw;
         const InT* src = xg + series * P.series_stride + wi * P.S;
+        if (segmented) {
+            int64_t s = P.starts[w], e = P.ends[w];
+            if (s < 0) s = 0;
+            if (e > P.n_total) e = P.n_total;
+            if (e < s) e = s;
+            series = 0;
+            wi = w;
+            src = xg + s;
+            n = static_cast<int>(e - s);
+            if (n < P.min_len || n < 1 || (P.need_hjorth && n < 2)) {     // windows.py:152-155: too short -> NaN
+                for (int j = r; j < P.n_features; j += G)
+                    store_cell<OutT>(P.out, wi * P.o_window + j * P.o_col, CUDART_NAN);
+                continue;                                                // group-uniform branch
+            }
+        }
+        int p2w = P.P2;                        // sort length of this window
+        if (segmented) {
+            p2w = 1;
+            while (p2w < n) p2w <<= 1;
+        }
         Group<G>::sync();                      // previous window's readers are done with buf
-        for (int i = r; i < P.P2; i += G) buf[i] = i < n ? src[i] : pos_inf<InT>();
+        for (int i = r; i < p2w; i += G) buf[i] = i < n ? src[i] : pos_inf<InT>();
         Group<G>::sync();
 
         double mob = 0.0, cpx = 0.0;
@@ -160,9 +185,9 @@ __global__ void __launch_bounds__(256) window_order_kernel(const OrderPlan P) {
         }
 
         if (P.need_sort) {
-            for (int k2 = 2; k2 <= P.P2; k2 <<= 1) {
+            for (int k2 = 2; k2 <= p2w; k2 <<= 1) {
                 for (int j = k2 >> 1; j > 0; j >>= 1) {
-                    for (int t = r; t < (P.P2 >> 1); t += G) {
+                    for (int t = r; t < (p2w >> 1); t += G) {
                         const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
                         const int l = i + j;
                         const InT a = buf[i], b = buf[l];
@@ -274,8 +299,94 @@ int32_t window_order_impl(const InT* x, const mhb_windows* geom, const int32_t* 
     return cuda_status(e, "window_order launch");
 }
 
+template <typename InT>
+int32_t segment_order_impl(const InT* x, int64_t n, const int64_t* starts, const int64_t* ends, int64_t n_windows,
+                           int64_t max_window_len, int64_t min_window_len, const int32_t* h_features,
+                           const double* h_params, int32_t n_features, const mhb_table* table, void* stream_v) {
+    MHB_REQUIRE(table, MHB_E_ARG, "segment_order: null table");
+    MHB_REQUIRE(n >= 0 && n_windows >= 0 && max_window_len >= 0, MHB_E_ARG, "segment_order: negative size");
+    MHB_REQUIRE(n_features >= 0 && n_features <= kMaxFeat, MHB_E_ARG, "segment_order: 0..%d features per call", kMaxFeat);
+    if (n_windows == 0 || n_features == 0) return MHB_OK;
+    MHB_REQUIRE(starts && ends && table->out && h_features && (x || n == 0), MHB_E_ARG, "segment_order: null pointer");
+    OrderPlan P;
+    memset(&P, 0, sizeof(P));
+    for (int j = 0; j < n_features; ++j) {
+        const int f = h_features[j];
+        MHB_REQUIRE(f >= MHB_F_MEDIAN && f <= MHB_F_HJORTH_COMPLEXITY, MHB_E_FEATURE,
+                    "segment_order: feature id %d is not in the order/derivative family", f);
+        P.feat[j] = f;
+        P.param[j] = h_params ? h_params[j] : 0.0;
+        if (f == MHB_F_PERCENTILE)
+            MHB_REQUIRE(P.param[j] >= 0.0 && P.param[j] <= 100.0, MHB_E_ARG,
+                        "segment_order: percentile q=%g outside [0, 100]", P.param[j]);
+        if (f == MHB_F_HJORTH_MOBILITY || f == MHB_F_HJORTH_COMPLEXITY) P.need_hjorth = 1;
+        else P.need_sort = 1;
+    }
+    P.n_features = n_features;
+    P.x = x;
+    P.nw = n_windows;
+    P.total_windows = n_windows;
+    P.starts = starts;
+    P.ends = ends;
+    P.n_total = n;
+    P.min_len = min_window_len;
+    int64_t p2 = 1;
+    while (p2 < max_window_len) p2 <<= 1;
+    MHB_REQUIRE(p2 * sizeof(InT) <= 192 * 1024, MHB_E_UNSUPPORTED,
+                "segment_order: windows of up to %lld samples do not fit one CTA's shared memory",
+                static_cast<long long>(max_window_len));
+    P.P2 = static_cast<int32_t>(p2);
+    P.W = static_cast<int32_t>(max_window_len);
+    P.S = 1;
+    P.out = table->out;
+    P.o_series = 0;
+    P.o_window = table->window_stride;
+    P.o_col = table->column_stride;
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+    const bool warp_mode = p2 * sizeof(InT) * 8 <= 96 * 1024;
+    const size_t smem = static_cast<size_t>(p2) * sizeof(InT) * (warp_mode ? 8 : 1);
+    const int64_t per_cta = warp_mode ? 8 : 1;
+    int64_t ctas = (n_windows + per_cta - 1) / per_cta;
+    const int64_t max_ctas = static_cast<int64_t>(kNumSMs) * 16;
+    if (ctas > max_ctas) ctas = max_ctas;
+    cudaError_t e;
+    const bool f32 = table->out_f32 != 0;
+#define MHB_GO(OUT, G)                                                                                       \
+    {                                                                                                        \
+        auto kern = window_order_kernel<InT, OUT, G>;                                                        \
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)); \
+        if (e == cudaSuccess) {                                                                              \
+            kern<<<static_cast<unsigned>(ctas), 256, smem, stream>>>(P);                                     \
+            e = cudaGetLastError();                                                                          \
+        }                                                                                                    \
+    }
+    if (warp_mode) {
+        if (f32) MHB_GO(float, 32) else MHB_GO(double, 32)
+    } else {
+        if (f32) MHB_GO(float, 256) else MHB_GO(double, 256)
+    }
+#undef MHB_GO
+    return cuda_status(e, "segment_order launch");
+}
+
 }  // namespace
 }  // namespace mhb
+
+extern "C" int32_t mhb_segment_order_f32(const float* x, int64_t n, const int64_t* starts, const int64_t* ends,
+                                         int64_t n_windows, int64_t max_window_len, int64_t min_window_len,
+                                         const int32_t* h_features, const double* h_params, int32_t n_features,
+                                         const mhb_table* table, void* stream) {
+    return mhb::segment_order_impl<float>(x, n, starts, ends, n_windows, max_window_len, min_window_len, h_features,
+                                          h_params, n_features, table, stream);
+}
+
+extern "C" int32_t mhb_segment_order_f64(const double* x, int64_t n, const int64_t* starts, const int64_t* ends,
+                                         int64_t n_windows, int64_t max_window_len, int64_t min_window_len,
+                                         const int32_t* h_features, const double* h_params, int32_t n_features,
+                                         const mhb_table* table, void* stream) {
+    return mhb::segment_order_impl<double>(x, n, starts, ends, n_windows, max_window_len, min_window_len, h_features,
+                                           h_params, n_features, table, stream);
+}
 
 extern "C" int32_t mhb_window_order_f32(const float* x, const mhb_windows* geom, const int32_t* h_features,
                                         const double* h_params, int32_t n_features, const mhb_table* table,

@@ -143,6 +143,122 @@ def window_table(x, wsize, wstep, features, zc_threshold=0.0, fs=1.0, out_dtype=
     return out[0] if was_1d else out
 
 
+def device_get_indices(index, wsize, wstep):
+    """get_indices (util/windows.py:162-178) on the device -> int64 cuda tensor [2, n_windows].
+
+    index: numpy / torch 1-D, integer, datetime64 / timedelta64 (same unit as wsize / wstep after conversion) or float.
+    """
+    torch = require_cuda()
+    lib = L.load()
+    if isinstance(index, torch.Tensor):
+        it = index if index.is_cuda else index.cuda()
+        if it.dtype.is_floating_point:
+            it = it.double()
+            first, last = float(it[0]), float(it[-1])
+        else:
+            it = it.long()
+            first, last = int(it[0]), int(it[-1])
+    else:
+        a = np.asarray(index)
+        if a.ndim != 1 or a.shape[0] == 0:
+            raise ValueError("get_indices: index must be a non-empty 1-D array")
+        if a.dtype.kind in "mM":
+            unit = np.datetime_data(a.dtype)[0]
+            if isinstance(wsize, np.timedelta64):
+                wsize = int(wsize.astype("timedelta64[%s]" % unit).astype(np.int64))
+            if isinstance(wstep, np.timedelta64):
+                wstep = int(wstep.astype("timedelta64[%s]" % unit).astype(np.int64))
+            a = a.view(np.int64)
+        if a.dtype.kind == "f":
+            a = a.astype(np.float64)
+            first, last = float(a[0]), float(a[-1])
+        elif a.dtype.kind in "iu":
+            a = a.astype(np.int64)
+            first, last = int(a[0]), int(a[-1])
+        else:
+            raise TypeError("get_indices: unsupported index dtype %s" % a.dtype)
+        it = torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    it = it.contiguous()
+    n = it.shape[0]
+    is_f = it.dtype == torch.float64
+    if is_f:
+        wsize, wstep = float(wsize), float(wstep)
+        if not wstep > 0:
+            raise ValueError("get_indices: wstep must be > 0")
+        nwin = max(0, int(math.ceil((last - first) / wstep)))       # len(np.arange(first, last, wstep))
+    else:
+        wsize, wstep = int(wsize), int(wstep)
+        if wstep <= 0:
+            raise ValueError("get_indices: wstep must be > 0")
+        nwin = len(range(first, last, wstep))
+    out = torch.empty((2, nwin), dtype=torch.int64, device=it.device)
+    if nwin:
+        fn = lib.mhb_get_indices_f64 if is_f else lib.mhb_get_indices_i64
+        st = fn(it.data_ptr(), n, first, wsize, wstep, nwin, out.data_ptr(), _stream_ptr(torch))
+        L.check(st, "get_indices")
+    return out
+
+
+def segment_table(x, indices, features, min_window_len=1, zc_threshold=0.0, out_dtype=None):
+    """Feature table of arbitrary [start, end) windows of ONE series (indices_rolling_apply,
+    util/windows.py:122-159).  indices: int64 [2, n] (numpy or cuda tensor).  Returns a cuda tensor
+    [n, len(features)]; rows of windows shorter than min_window_len are NaN."""
+    torch = require_cuda()
+    lib = L.load()
+    t, _, was_1d = to_device_series(x)
+    if not was_1d and t.shape[0] != 1:
+        raise ValueError("index-addressed windows take a 1-D array")
+    t = t.reshape(-1)
+    n = t.shape[0]
+    if isinstance(indices, torch.Tensor):
+        ind = indices.to(device=t.device, dtype=torch.int64)
+    else:
+        ia = np.asarray(indices)
+        if ia.ndim != 2 or ia.shape[0] != 2:
+            raise ValueError("indices must have shape (2, n)")
+        ind = torch.from_numpy(np.ascontiguousarray(ia.astype(np.int64))).to(t.device)
+    if ind.dim() != 2 or ind.shape[0] != 2:
+        raise ValueError("indices must have shape (2, n)")
+    ind = ind.contiguous()
+    nwin = ind.shape[1]
+    nf = len(features)
+    if out_dtype is None:
+        out_dtype = torch.float64
+    out = torch.empty((nwin, nf), dtype=out_dtype, device=t.device)
+    if nwin == 0 or nf == 0:
+        return out
+    starts_ptr = ind.data_ptr()
+    ends_ptr = ind.data_ptr() + nwin * 8
+    stream = _stream_ptr(torch)
+    f32_in = t.dtype == torch.float32
+    by_family = {"stream": [], "order": []}
+    for j, f in enumerate(features):
+        if f.family not in by_family:
+            raise NotImplementedError("spectral reducers are defined on uniform windows only")
+        by_family[f.family].append(j)
+    max_len = None
+    for family, cols in by_family.items():
+        for run in _runs(cols):
+            j0 = run[0]
+            tab = L.MhbTable(out.data_ptr() + j0 * out.element_size(), 1 if out.dtype == torch.float32 else 0,
+                             0, out.stride(0), out.stride(1))
+            ids = L.i32_array([features[j].fid for j in run])
+            if family == "stream":
+                fn = lib.mhb_segment_stats_f32 if f32_in else lib.mhb_segment_stats_f64
+                st = fn(t.data_ptr(), n, starts_ptr, ends_ptr, nwin, int(min_window_len), ids, len(run),
+                        float(zc_threshold), C.byref(tab), stream)
+            else:
+                if max_len is None:
+                    lens = ind[1].clamp(max=n) - ind[0].clamp(min=0)
+                    max_len = max(0, int(lens.max().item()))
+                fn = lib.mhb_segment_order_f32 if f32_in else lib.mhb_segment_order_f64
+                pars = L.f64_array([features[j].params[0] if features[j].params else 0.0 for j in run])
+                st = fn(t.data_ptr(), n, starts_ptr, ends_ptr, nwin, max_len, int(min_window_len), ids, pars,
+                        len(run), C.byref(tab), stream)
+            L.check(st, "segment_%s" % family)
+    return out
+
+
 def _runs(cols):
     runs, cur = [], []
     for c in cols:

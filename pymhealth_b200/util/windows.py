@@ -17,7 +17,7 @@ import numpy as np
 from numpy.lib.stride_tricks import as_strided
 
 from .. import _lib as L
-from ..engine import window_table
+from ..engine import device_get_indices, segment_table, window_table
 from ..reducers import resolve
 
 
@@ -98,6 +98,66 @@ def _rolling_apply_dict(funcs, wsize: Optional[int] = None, wstep: int = 1) -> C
     return dict_funcs_rolling_apply
 
 
-def nonuniform_rolling_apply(func, min_window_len: int = 1):
-    """Timestamp-indexed windows (windows.py:181-249) -- scheduled for the next round."""
-    raise NotImplementedError("nonuniform_rolling_apply: the non-uniform window kernels are not built yet")
+def get_indices(index: np.ndarray, wsize, wstep) -> np.ndarray:
+    """Start and end indices of the windows ``[t0 + k*wstep, t0 + k*wstep + wsize)`` over a sorted index
+    (windows.py:162-178): device binary search, int64[2, n] back on the host."""
+    return device_get_indices(index, wsize, wstep).cpu().numpy()
+
+
+def _segment_apply(features, indices, arr, min_window_len):
+    a = np.asarray(arr)
+    if a.ndim != 1:
+        raise ValueError("index-addressed windows take a 1-D array")
+    tab = segment_table(a, indices, features, min_window_len=min_window_len, zc_threshold=_zc_threshold(features))
+    res = tab.cpu().numpy()
+    # windows.py:149: the output has the dtype of ``arr``; for integer input the reference stores NaN into an
+    # integer array (garbage, SURVEY 3.2) -- float64 is returned instead
+    if a.dtype == np.float32:
+        res = res.astype(np.float32)
+    return res
+
+
+@lru_cache(256)
+def indices_rolling_apply(func: Callable, min_window_len: int = 1) -> Callable:
+    """Callable ``(indices[2, n], arr)`` applying ``func`` to ``arr[start:end]`` (windows.py:122-159)."""
+    feature, _ = resolve(func)
+
+    def windows_loop(indices, arr, min_window_len=min_window_len):
+        return np.ascontiguousarray(_segment_apply([feature], indices, arr, min_window_len)[:, 0])
+    windows_loop.__doc__ = "Apply the '%s' function to windows with known indices (CUDA)." % getattr(func, "__name__", func)
+    return windows_loop
+
+
+@singledispatch
+def nonuniform_rolling_apply(func: Callable, min_window_len: int = 1) -> Callable:
+    """Moving-window aggregation over a non-uniform (e.g. datetime) index (windows.py:181-216):
+    returns ``moving_window(index, arr, wsize, wstep[, min_window_len])``."""
+    feature, _ = resolve(func)
+
+    def moving_window(index, arr, wsize, wstep, min_window_len=min_window_len):
+        indices = device_get_indices(index, wsize, wstep)           # stays on the device
+        return np.ascontiguousarray(_segment_apply([feature], indices, arr, min_window_len)[:, 0])
+    moving_window.__doc__ = "Aggregate windows with the '%s' function (CUDA)." % getattr(func, "__name__", func)
+    return moving_window
+
+
+@nonuniform_rolling_apply.register(list)
+@nonuniform_rolling_apply.register(tuple)
+def _nu_rolling_apply_coll(funcs, min_window_len: int = 1) -> Callable:
+    features = [resolve(f)[0] for f in funcs]
+
+    def moving_window(index, arr, wsize, wstep):
+        indices = device_get_indices(index, wsize, wstep)
+        tab = _segment_apply(features, indices, arr, min_window_len)     # every reducer in one pass
+        return [np.ascontiguousarray(tab[:, j]) for j in range(len(features))]
+    return moving_window
+
+
+@nonuniform_rolling_apply.register(dict)
+def _nu_rolling_apply_dict(funcs, min_window_len: int = 1) -> Callable:
+    names = list(funcs.keys())
+    inner = _nu_rolling_apply_coll(list(funcs.values()), min_window_len)
+
+    def moving_window(index, arr, wsize, wstep):
+        return dict(zip(names, inner(index, arr, wsize, wstep)))
+    return moving_window
