@@ -144,37 +144,59 @@ __device__ __forceinline__ double round_down_threshold<double>(double th) {
     return th;
 }
 
-// Stage geometry (no divisions in the stage loop).
+// Chunk / stage geometry.  Everything a stage needs is 32-bit arithmetic relative to the chunk start (a chunk is
+// at most 64 stages of <= 24 KB); the 64-bit quantities are folded once per CTA.
+template <typename InT>
+struct ChunkDesc {
+    static constexpr int A = 16 / sizeof(InT);
+    int64_t goff0;      // global element offset of the chunk's first sample
+    int32_t lead0;      // goff0 mod A
+    int32_t avail;      // samples of the series from the chunk start on (clamped)
+    int32_t room;       // elements of the whole buffer from the aligned chunk start on (clamped)
+    __device__ __forceinline__ void set(const StatsPlan& P, int64_t series_base, int64_t chunk_s0) {
+        goff0 = series_base + chunk_s0;
+        lead0 = static_cast<int32_t>(goff0 & (A - 1));
+        const int64_t av = P.series_len - chunk_s0;
+        avail = av > 0x7fffffff ? 0x7fffffff : static_cast<int32_t>(av);
+        const int64_t rm = P.total_elems - (goff0 - lead0);
+        room = rm > 0x7fffffff ? 0x7fffffff : static_cast<int32_t>(rm);
+    }
+};
+
 template <typename InT>
 struct StageDesc {
     static constexpr int A = 16 / sizeof(InT);
-    int64_t goff;       // global element offset of the stage's first sample
-    int32_t lead;       // goff - aligned-down offset
+    int32_t rel;        // first sample of the stage, relative to the chunk start
+    int32_t lead;       // (goff0 + rel) mod A: offset of the stage's first sample inside the staged copy
     int32_t nblk;       // blocks in this stage
     int32_t cnt;        // samples belonging to blocks
     int32_t has_next;   // the sample after the stage exists in the series
     int32_t n_load;     // elements copied by TMA (multiple of 16 bytes)
     int32_t tma;        // stage is loaded by TMA (else cooperative guarded copy)
 
-    __device__ __forceinline__ void set(const StatsPlan& P, int64_t series_base, int64_t s0, int32_t blocks_left) {
-        nblk = blocks_left < P.TB ? blocks_left : P.TB;
+    __device__ __forceinline__ void set(const StatsPlan& P, const ChunkDesc<InT>& ck, int32_t st, int32_t stage_samples,
+                                        int32_t blocks_left, int32_t TB) {
+        nblk = blocks_left < TB ? blocks_left : TB;
         cnt = nblk * P.g;
-        has_next = (s0 + cnt < P.series_len) ? 1 : 0;
-        goff = series_base + s0;
-        lead = static_cast<int32_t>(goff & (A - 1));
+        rel = st * stage_samples;
+        has_next = (rel + cnt < ck.avail) ? 1 : 0;
+        lead = (ck.lead0 + rel) & (A - 1);
         n_load = (lead + cnt + has_next + A - 1) & ~(A - 1);
-        tma = (P.use_tma && (goff - lead) + n_load <= P.total_elems) ? 1 : 0;
+        tma = (P.use_tma && (ck.lead0 + rel - lead) + n_load <= ck.room) ? 1 : 0;
     }
 };
 
 __device__ __forceinline__ int wrap(int i, int n) { return i >= n ? i - n : i; }
 
 // ---------------------------------------------------------------------------------------------
-template <typename InT, typename OutT, bool M4, bool TD, int MCELL /*0 = runtime m; -8 = 2 x float4*/>
+// GEO = 1: the hot geometry (cpb = 10, k = 2, hop = 1, TB = 25 -- W = 500 / S = 250 with 25-sample cells) with every
+// loop bound known at compile time; GEO = 0: bounds from the plan.
+template <typename InT, typename OutT, bool M4, bool TD, int MCELL /*0 = runtime m; -8 = 2 x float4*/, int GEO>
 __global__ void __launch_bounds__(kThreads, 3) window_stats_kernel(const StatsPlan P) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int tid = threadIdx.x;
     const int m = MCELL > 0 ? MCELL : (MCELL < 0 ? -MCELL : P.m);
+    const int g_cpb = GEO ? 10 : P.cpb, g_k = GEO ? 2 : P.k, g_hop = GEO ? 1 : P.hop, g_TB = GEO ? 25 : P.TB;
     using Part = Partials<InT, M4, TD>;
 
     // ---- carve shared memory
@@ -182,9 +204,9 @@ __global__ void __launch_bounds__(kThreads, 3) window_stats_kernel(const StatsPl
     unsigned char* ptr = smem_raw + 128;
     InT* stage_buf = reinterpret_cast<InT*>(ptr);
     ptr += static_cast<size_t>(P.NS) * P.stage_elems * sizeof(InT);
-    const int ncell_max = P.TB * P.cpb;
+    const int ncell_max = g_TB * g_cpb;
     Part cell, ring;
-    if (P.cpb > 1) ptr = cell.carve(ptr, ncell_max);
+    if (g_cpb > 1) ptr = cell.carve(ptr, ncell_max);
     ptr = ring.carve(ptr, P.RB);
     double* pre = reinterpret_cast<double*>(ptr);                           // [kNPre][RB + 1] (k > kDirectK)
     const int R1 = P.RB + 1;
@@ -196,13 +218,16 @@ __global__ void __launch_bounds__(kThreads, 3) window_stats_kernel(const StatsPl
     const int64_t w0 = static_cast<int64_t>(chunk) * P.win_per_chunk;
     const int64_t w1 = min(P.nw, w0 + P.win_per_chunk);
     const int32_t nwin = static_cast<int32_t>(w1 - w0);
-    const int32_t n_blocks = (nwin - 1) * P.hop + P.k;
-    const int32_t n_stages = (n_blocks + P.TB - 1) / P.TB;
-    const bool use_prefix = P.k > kDirectK;
+    const int32_t n_blocks = (nwin - 1) * g_hop + g_k;
+    const int32_t n_stages = (n_blocks + g_TB - 1) / g_TB;
+    const bool use_prefix = g_k > kDirectK;
     const InT* xg = reinterpret_cast<const InT*>(P.x);
     const int64_t series_base = series * P.series_stride;
     const int64_t chunk_s0 = w0 * P.S;                    // first sample of the chunk (series-relative)
-    const int32_t stage_samples = P.TB * P.g;
+    const int32_t stage_samples = g_TB * P.g;
+    ChunkDesc<InT> ck;
+    ck.set(P, series_base, chunk_s0);
+    const InT* xck = xg + ck.goff0;                       // chunk start
 
     if (tid == 0) {
         for (int i = 0; i < P.NS; ++i) mbar_init(&full[i], 1);
@@ -215,10 +240,10 @@ __global__ void __launch_bounds__(kThreads, 3) window_stats_kernel(const StatsPl
     if (tid == 0) {
         for (int st = 0; st < P.NS && st < n_stages; ++st) {
             StageDesc<InT> d;
-            d.set(P, series_base, chunk_s0 + static_cast<int64_t>(st) * stage_samples, n_blocks - st * P.TB);
+            d.set(P, ck, st, stage_samples, n_blocks - st * g_TB, g_TB);
             if (d.tma) {
                 mbar_arrive_expect_tx(&full[st], d.n_load * sizeof(InT));
-                bulk_g2s(stage_buf + static_cast<size_t>(st) * P.stage_elems, xg + (d.goff - d.lead),
+                bulk_g2s(stage_buf + static_cast<size_t>(st) * P.stage_elems, xck + (d.rel - d.lead),
                          d.n_load * sizeof(InT), &full[st]);
             }
         }
@@ -236,21 +261,21 @@ __global__ void __launch_bounds__(kThreads, 3) window_stats_kernel(const StatsPl
 
     for (int st = 0; st < n_stages; ++st) {
         StageDesc<InT> d;
-        d.set(P, series_base, chunk_s0 + static_cast<int64_t>(st) * stage_samples, n_blocks - st * P.TB);
+        d.set(P, ck, st, stage_samples, n_blocks - st * g_TB, g_TB);
         InT* buf = stage_buf + static_cast<size_t>(slot) * P.stage_elems;
         if (d.tma) {
             mbar_wait(&full[slot], parity);
         } else {
             // guarded cooperative copy: unaligned base pointer or the last few samples of the buffer
             const int n = d.cnt + d.has_next;
-            for (int i = tid; i < n; i += kThreads) buf[d.lead + i] = xg[d.goff + i];
+            for (int i = tid; i < n; i += kThreads) buf[d.lead + i] = xck[d.rel + i];
             __syncthreads();
         }
         const InT* s = buf + d.lead;
         if (st == 0) c = static_cast<double>(s[0]);
 
         // ---------------- phase 1: one cell per thread
-        const int ncell = d.nblk * P.cpb;
+        const int ncell = d.nblk * g_cpb;
         for (int ce = tid; ce < ncell; ce += kThreads) {
             const InT* p = s + ce * m;
             CellAcc<InT> a;
@@ -312,8 +337,8 @@ __global__ void __launch_bounds__(kThreads, 3) window_stats_kernel(const StatsPl
                 llb = fabsf(static_cast<float>(nx - prev));
                 zcb = ((nx > th) != (prev > th)) ? 1.f : 0.f;
             }
-            const Part& dst = (P.cpb > 1) ? cell : ring;
-            const int idx = (P.cpb > 1) ? ce : wrap(ring_head + ce, P.RB);
+            const Part& dst = (g_cpb > 1) ? cell : ring;
+            const int idx = (g_cpb > 1) ? ce : wrap(ring_head + ce, P.RB);
             dst.s1[idx] = a.s1;
             dst.s2[idx] = a.s2;
             if (M4) {
@@ -334,11 +359,10 @@ __global__ void __launch_bounds__(kThreads, 3) window_stats_kernel(const StatsPl
         // ---------------- refill this slot with stage st + NS
         if (tid == 0 && st + P.NS < n_stages) {
             StageDesc<InT> nd;
-            nd.set(P, series_base, chunk_s0 + static_cast<int64_t>(st + P.NS) * stage_samples,
-                   n_blocks - (st + P.NS) * P.TB);
+            nd.set(P, ck, st + P.NS, stage_samples, n_blocks - (st + P.NS) * g_TB, g_TB);
             if (nd.tma) {
                 mbar_arrive_expect_tx(&full[slot], nd.n_load * sizeof(InT));
-                bulk_g2s(buf, xg + (nd.goff - nd.lead), nd.n_load * sizeof(InT), &full[slot]);
+                bulk_g2s(buf, xck + (nd.rel - nd.lead), nd.n_load * sizeof(InT), &full[slot]);
             }
         }
         if (++slot == P.NS) {
@@ -347,7 +371,7 @@ __global__ void __launch_bounds__(kThreads, 3) window_stats_kernel(const StatsPl
         }
 
         // ---------------- phase 2: cells -> blocks; one (block, quantity pair) per thread
-        if (P.cpb > 1) {
+        if (g_cpb > 1) {
             constexpr int NG = 2 + (M4 ? 1 : 0) + (TD ? 2 : 0);     // {s1,s2} {mn,mx} [{s3,s4}] [{ll,llb} {zc,zcb}]
             const int total = d.nblk * NG;
             for (int idx = tid; idx < total; idx += kThreads) {
@@ -356,11 +380,11 @@ __global__ void __launch_bounds__(kThreads, 3) window_stats_kernel(const StatsPl
                     b -= d.nblk;
                     ++grp;
                 }
-                const int c0 = b * P.cpb;
+                const int c0 = b * g_cpb;
                 const int r = wrap(ring_head + b, P.RB);
                 if (grp == 0) {
                     double u = 0, v = 0;
-                    for (int i = 0; i < P.cpb; ++i) {
+                    for (int i = 0; i < g_cpb; ++i) {
                         u += cell.s1[c0 + i];
                         v += cell.s2[c0 + i];
                     }
@@ -368,7 +392,7 @@ __global__ void __launch_bounds__(kThreads, 3) window_stats_kernel(const StatsPl
                     ring.s2[r] = v;
                 } else if (grp == 1) {
                     InT u = cell.mn[c0], v = cell.mx[c0];
-                    for (int i = 1; i < P.cpb; ++i) {
+                    for (int i = 1; i < g_cpb; ++i) {
                         u = tmin<InT>(u, cell.mn[c0 + i]);
                         v = tmax<InT>(v, cell.mx[c0 + i]);
                     }
@@ -376,7 +400,7 @@ __global__ void __launch_bounds__(kThreads, 3) window_stats_kernel(const StatsPl
                     ring.mx[r] = v;
                 } else if (M4 && grp == 2) {
                     double u = 0, v = 0;
-                    for (int i = 0; i < P.cpb; ++i) {
+                    for (int i = 0; i < g_cpb; ++i) {
                         u += cell.s3[c0 + i];
                         v += cell.s4[c0 + i];
                     }
@@ -384,14 +408,14 @@ __global__ void __launch_bounds__(kThreads, 3) window_stats_kernel(const StatsPl
                     ring.s4[r] = v;
                 } else if (TD && grp == (M4 ? 3 : 2)) {
                     double u = 0;                    // float cell terms, float64 across cells
-                    for (int i = 0; i < P.cpb; ++i) u += static_cast<double>(cell.ll[c0 + i]);
+                    for (int i = 0; i < g_cpb; ++i) u += static_cast<double>(cell.ll[c0 + i]);
                     ring.ll[r] = static_cast<float>(u);
-                    ring.llb[r] = cell.llb[c0 + P.cpb - 1];
+                    ring.llb[r] = cell.llb[c0 + g_cpb - 1];
                 } else if (TD) {
                     float u = 0;
-                    for (int i = 0; i < P.cpb; ++i) u += cell.zc[c0 + i];
+                    for (int i = 0; i < g_cpb; ++i) u += cell.zc[c0 + i];
                     ring.zc[r] = u;
-                    ring.zcb[r] = cell.zcb[c0 + P.cpb - 1];
+                    ring.zcb[r] = cell.zcb[c0 + g_cpb - 1];
                 }
             }
             __syncthreads();
@@ -408,7 +432,7 @@ __global__ void __launch_bounds__(kThreads, 3) window_stats_kernel(const StatsPl
                 const double* srcd = q == 0 ? ring.s1 : q == 1 ? ring.s2 : (M4 && q == 2) ? ring.s3 : ring.s4;
                 const float* srcf = (q == nq - 2) ? ring.ll : ring.zc;
                 double run = carry[q];
-                int pslot = (pre_emit + (blocks_done - emitted * P.hop)) % R1;   // prefix slot of block blocks_done
+                int pslot = (pre_emit + (blocks_done - emitted * g_hop)) % R1;   // prefix slot of block blocks_done
                 if (pslot < 0) pslot += R1;
                 for (int base = 0; base < d.nblk; base += 32) {
                     const int b = base + lane;
@@ -434,15 +458,15 @@ __global__ void __launch_bounds__(kThreads, 3) window_stats_kernel(const StatsPl
 
         // ---------------- phase 3: finished windows (deferred until `flush` are pending)
         int32_t ready = 0;
-        if (blocks_done >= P.k) {
-            ready = (blocks_done - P.k) / P.hop + 1;
+        if (blocks_done >= g_k) {
+            ready = (blocks_done - g_k) / g_hop + 1;
             ready = ready < nwin ? ready : nwin;
         }
         const bool do_flush = (ready - emitted >= P.flush) || (st == n_stages - 1);
         if (do_flush) {
             constexpr int nq = 2 + (M4 ? 2 : 0) + (TD ? 2 : 0);
             for (int wl = emitted + tid; wl < ready; wl += kThreads) {
-                const int rel = (wl - emitted) * P.hop;          // < RB by construction
+                const int rel = (wl - emitted) * g_hop;          // < RB by construction
                 const int r0 = wrap(ring_emit + rel, P.RB);
                 double S1, S2, S3 = 0, S4 = 0, LL = 0, ZC = 0;
                 InT mn = ring.mn[r0], mx = ring.mx[r0];
@@ -458,7 +482,7 @@ __global__ void __launch_bounds__(kThreads, 3) window_stats_kernel(const StatsPl
                         LL = ring.ll[r0];
                         ZC = ring.zc[r0];
                     }
-                    for (int j = 1; j < P.k; ++j) {
+                    for (int j = 1; j < g_k; ++j) {
                         r = wrap(r + 1, P.RB);
                         S1 += ring.s1[r];
                         S2 += ring.s2[r];
@@ -475,7 +499,7 @@ __global__ void __launch_bounds__(kThreads, 3) window_stats_kernel(const StatsPl
                     }
                 } else {
                     const int lo = wrap(pre_emit + rel, R1);
-                    int hi = lo + P.k;
+                    int hi = lo + g_k;
                     while (hi >= R1) hi -= R1;
                     S1 = pre[0 * R1 + hi] - pre[0 * R1 + lo];
                     S2 = pre[1 * R1 + hi] - pre[1 * R1 + lo];
@@ -487,7 +511,7 @@ __global__ void __launch_bounds__(kThreads, 3) window_stats_kernel(const StatsPl
                         LL = pre[(nq - 2) * R1 + hi] - pre[(nq - 2) * R1 + lo];
                         ZC = pre[(nq - 1) * R1 + hi] - pre[(nq - 1) * R1 + lo];
                     }
-                    for (int j = 1; j < P.k; ++j) {
+                    for (int j = 1; j < g_k; ++j) {
                         r = wrap(r + 1, P.RB);
                         mn = tmin<InT>(mn, ring.mn[r]);
                         mx = tmax<InT>(mx, ring.mx[r]);
@@ -538,7 +562,7 @@ __global__ void __launch_bounds__(kThreads, 3) window_stats_kernel(const StatsPl
                     store_cell<OutT>(P.out, obase + j * P.o_col, v);
                 }
             }
-            const int adv = (ready - emitted) * P.hop;       // blocks released (may exceed RB when hop > k)
+            const int adv = (ready - emitted) * g_hop;       // blocks released (may exceed RB when hop > k)
             ring_emit = (ring_emit + adv) % P.RB;
             pre_emit = (pre_emit + adv) % R1;
             emitted = ready;
@@ -546,7 +570,7 @@ __global__ void __launch_bounds__(kThreads, 3) window_stats_kernel(const StatsPl
         // The next iteration writes ring / prefix slots of NEW blocks only after a barrier that every
         // thread reaches after finishing this phase (cpb > 1: the barrier after phase 1); when phase 1
         // itself writes the ring, close the iteration with one.
-        if (P.cpb == 1) __syncthreads();
+        if (g_cpb == 1) __syncthreads();
     }
 }
 
@@ -584,19 +608,22 @@ CellChoice choose_cell(int64_t g, bool allow_vec4) {
 
 template <typename InT, typename OutT, bool M4, bool TD>
 cudaError_t launch_with_cell(const StatsPlan& P, int mt, dim3 grid, size_t smem, cudaStream_t stream) {
-#define MHB_LAUNCH(MC)                                                                                  \
+#define MHB_LAUNCH(MC, GEO)                                                                             \
     {                                                                                                   \
-        auto kern = window_stats_kernel<InT, OutT, M4, TD, MC>;                                         \
+        auto kern = window_stats_kernel<InT, OutT, M4, TD, MC, GEO>;                                    \
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
         if (e != cudaSuccess) return e;                                                                 \
         kern<<<grid, kThreads, smem, stream>>>(P);                                                      \
         return cudaGetLastError();                                                                      \
     }
     if (mt == -8) {
-        if constexpr (sizeof(InT) == 4) MHB_LAUNCH(-8)
+        if constexpr (sizeof(InT) == 4) MHB_LAUNCH(-8, 0)
     }
-    if (mt == 25) MHB_LAUNCH(25)
-    MHB_LAUNCH(0)
+    if (mt == 25) {
+        if (P.cpb == 10 && P.k == 2 && P.hop == 1 && P.TB == 25) MHB_LAUNCH(25, 1)
+        MHB_LAUNCH(25, 0)
+    }
+    MHB_LAUNCH(0, 0)
 #undef MHB_LAUNCH
 }
 
@@ -640,7 +667,7 @@ int32_t window_stats_impl(const InT* x, const mhb_windows* geom, const int32_t* 
 
     // block size: a divisor of gcd(W, S) small enough for one stage, with k + hop bounded
     int64_t g = gcd64(P.W, P.S);
-    constexpr int64_t kMaxStageBytes = 24 * 1024;
+    constexpr int64_t kMaxStageBytes = 25 * 1024;      // 25 blocks of 250 float32 samples fit one stage
     const int64_t max_block = kMaxStageBytes / static_cast<int64_t>(sizeof(InT));
     if (g > max_block) {
         int64_t best = 1;
