@@ -53,6 +53,20 @@ def feature_list():
     return stream, spec
 
 
+def ncu_traffic(nsub):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures of the bench
+    launches (profiles/ncu_traffic.json, written by tools/ncu_traffic.py from the .ncu-rep files); {} when absent or
+    taken at another shard size."""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    try:
+        d = json.load(open(p))
+    except Exception:
+        return {}
+    if int(d.get("subjects_per_gpu", -1)) != int(nsub):
+        return {}
+    return {k: v for k, v in d.get("traffic_bytes_per_launch", {}).items()}
+
+
 def measured_peak_gbs():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -297,18 +311,24 @@ def run_b200_arm(args):
         peak, peak_src = measured_peak_gbs()
         samples_b = nsub * 3 * n * 4
 
-        def roof(name, ms, ncols):
+        traffic = ncu_traffic(nsub)
+
+        def roof(name, key, ms, ncols):
             alg = samples_b + windows_per_step * ncols * 4
             ach = alg / (ms * 1e-3) / 1e9
             return {"kernel": name, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                    "traffic": None, "ms_per_launch": ms, "algorithmic_bytes": alg, "peak_source": peak_src}
-        k_stats = roof("window_stats_kernel (kernel 1a)", ms_stats, len(stream_f))
-        k_spec = roof("window_spectral_kernel (kernel 2)", ms_spec, len(spec_f))
+                    "traffic": traffic.get(key), "ms_per_launch": ms, "algorithmic_bytes": alg, "peak_source": peak_src}
+        k_stats = roof("window_stats_kernel (kernel 1a)", "window_stats", ms_stats, len(stream_f))
+        k_spec = roof("spectral_fast_kernel (kernel 2)", "window_spectral", ms_spec, len(spec_f))
         dominant = k_spec if ms_spec >= ms_stats else k_stats
         dominant = dict(dominant)
-        if dominant is not None and dominant["kernel"].startswith("window_spectral"):
-            dominant["note"] = ("kernel 2 is FP32-issue-bound (a 250-point complex FFT per 1,000 B window), not HBM-bound; "
-                                "frac is its HBM fraction all the same.  kernel 1a (HBM-bound) is listed under 'kernels'.")
+        if dominant["kernel"].startswith("spectral"):
+            # FP32 lane-instructions the transform needs at the very least: ~16e3 per window
+            fp32_peak = 148 * 128 * (clocks or {}).get("sm_mhz", 1965.0) * 1e6 if clocks else 148 * 128 * 1965e6
+            dominant["note"] = ("kernel 2 is FP32-issue-bound (a 250-point complex FFT + PSD reducers per 1,000 B window is >= ~16e3 "
+                                "lane-instructions; 100 %% FP32 issue would be ~35 %% of HBM peak), not HBM-bound; frac is its HBM "
+                                "fraction all the same.  kernel 1a (HBM-bound) is listed under 'kernels'.")
+            dominant["fp32_issue_floor_frac"] = (windows_per_step * 16e3 / fp32_peak) / (ms_spec * 1e-3)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

@@ -1,6 +1,6 @@
 #!/bin/bash
 # One GPU session: parity tests, smoke, both bench arms, ncu launch list of the bench command, and ncu --set full
-# captures of the two bench kernels on a small input.  Outputs land in gpurun_out/.
+# captures of the two bench kernels at bench shard size.  Outputs land in gpurun_out/.
 set -u
 mkdir -p gpurun_out
 R=${ROUND:-r1}
@@ -14,8 +14,8 @@ if [ $rc -eq 0 ]; then
       --log-file gpurun_out/launches_$R.csv python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_launches_$R.log 2>&1
   echo "ncu launches rc=$?"
 fi
-python tools/ncu_target.py c3_full > gpurun_out/plain_full.log 2>&1 && \
-  ncu --set full --clock-control none --import-source on -k regex:window_stats -s 1 -c 1 -o gpurun_out/prof_stats_$R python tools/ncu_target.py c3_full > gpurun_out/ncu_stats_$R.log 2>&1
-python tools/ncu_target.py c3_spec > gpurun_out/plain_spec.log 2>&1 && \
-  ncu --set full --clock-control none --import-source on -k regex:spectral_ -s 1 -c 1 -o gpurun_out/prof_spec_$R python tools/ncu_target.py c3_spec > gpurun_out/ncu_spec_$R.log 2>&1
+NSUB=125 python tools/ncu_target.py c3_full > gpurun_out/plain_full.log 2>&1 && \
+  NSUB=125 ncu --set full --clock-control none --import-source on -k regex:window_stats -s 1 -c 1 -o gpurun_out/prof_stats_$R python tools/ncu_target.py c3_full > gpurun_out/ncu_stats_$R.log 2>&1
+NSUB=125 python tools/ncu_target.py c3_spec > gpurun_out/plain_spec.log 2>&1 && \
+  NSUB=125 ncu --set full --clock-control none --import-source on -k regex:spectral_ -s 1 -c 1 -o gpurun_out/prof_spec_$R python tools/ncu_target.py c3_spec > gpurun_out/ncu_spec_$R.log 2>&1
 echo done

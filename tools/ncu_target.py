@@ -18,7 +18,8 @@ def main():
             stats.drange.feature(), stats.skewness.feature(), stats.kurtosis.feature(),
             timedom.zero_crossing_count.feature(0.0), timedom.line_length.feature()]
     if what.startswith("c3"):
-        x = synth.device_accelerometer(2, 30_240_000, dev).view(6, -1)
+        nsub = int(os.environ.get("NSUB", "2"))
+        x = synth.device_accelerometer(nsub, 30_240_000, dev).view(nsub * 3, -1)
         W, S = 500, 250
     elif what.startswith("c4"):
         x = synth.device_ppg(32, 5_529_600, dev)
