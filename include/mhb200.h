@@ -175,6 +175,26 @@ int32_t mhb_psd_reduce_f64(const double* psd, const double* freqs, int64_t n_row
 int32_t mhb_window_psd_f32(const float* x, const mhb_windows* geom, void* psd_out, int32_t out_f32,
                            void* stream);
 
+/* ---- accelerometer pre-stage (src/mhealth/inertial/accelerometer.py) --------------------------------
+ * op 0 magnitude(x, y, z) :198-225 -> output of the input type (float32 arithmetic for float32, bit-identical);
+ * op 1 roll(y, z) :13-25 and op 2 pitch(x, y, z) :44-56 -> float64 degrees (arctan2 in the input type).
+ * x may be NULL for roll. */
+int32_t mhb_accel_elementwise(int32_t op, int32_t is_f64, const void* x, const void* y, const void* z, int64_t n,
+                              void* out, void* stream);
+/* magnitude_dot(x, y, z) :236-259 = sqrt(x.x + y.y + z.z) -> out[0] (float64 accumulation, fixed order).
+ * workspace: mhb_accel_sumsq_workspace(n) doubles. */
+int64_t mhb_accel_sumsq_workspace(int64_t n);
+int32_t mhb_accel_magnitude_dot(int32_t is_f64, const void* x, const void* y, const void* z, int64_t n,
+                                double* workspace, int64_t workspace_len, double* out, void* stream);
+
+/* ---- successive-difference statistics (HRV time-domain metrics, src/mhealth/heart/hrv.py:111-170) ---------
+ * out6 = {n - 1, sum(diff), mean(diff), var(diff) (population), count(|diff| > abs_threshold), mean(diff^2)}:
+ * pnnx = out[4] / out[0], rmssd = sqrt(out[5]), ssd = out[1], sdsd = sqrt(out[3]).
+ * workspace: mhb_diff_stats_workspace(n - 1) doubles. */
+int64_t mhb_diff_stats_workspace(int64_t n_diff);
+int32_t mhb_diff_stats_f64(const double* x, int64_t n, double abs_threshold, double* workspace, int64_t workspace_len,
+                           double* out6, void* stream);
+
 /* ---- kernel 3: location traces -------------------------------------------------------------
  * haversine gufuncs, location/distance.py:22-59 (float64 only, like the reference). */
 int32_t mhb_haversine_elementwise(const double* lat1, const double* lon1, const double* lat2,

@@ -1,5 +1,5 @@
 """Frequency-domain PSD reducers of ``mhealth.heart.hrv`` (reference src/mhealth/heart/hrv.py:172-198).
-The RR-interval time-domain metrics of that module are out of the hot path."""
+and, below them, its RR-interval time-domain metrics (hrv.py:24-170) as thin wrappers over the same kernels."""
 import numpy as np
 
 from .. import _lib as L
@@ -28,3 +28,102 @@ def peak_frequency(psd, freqs, lower=None, upper=None):
         above = f[f > upper]
         hi = float(above.min()) if above.size else None     # inclusive upper bound -> exclusive bound at the next bin
     return float(psd_reduce(psd, freqs, [(L.S_PEAK_FREQUENCY, lower, hi)])[0])
+
+
+# ---------------------------------------------------------------------------------------------------------
+# Time-domain metrics on normal R-peak intervals (hrv.py:24-170): thin host wrappers over the window-statistics and
+# successive-difference kernels.
+def td_factor(unit: str) -> float:
+    """Nanoseconds per ``unit`` (hrv.py:24-34)."""
+    try:
+        return {"ns": 1., "us": 1e3, "ms": 1e6, "s": 1e9}[unit]
+    except KeyError:
+        raise ValueError('Unknown unit. Must be: "ns", "us", "ms", or "s"')
+
+
+def nni_to_ms(nni, current_unit: str = 'ns'):
+    """hrv.py:37-39."""
+    return td_factor(current_unit) * np.asarray(nni).astype(float) / 1e6
+
+
+def _diff_stats(nni, threshold=0.0):
+    import ctypes as C                                   # noqa: F401
+    from ..engine import require_cuda, _stream_ptr
+    torch = require_cuda()
+    a = np.ascontiguousarray(np.asarray(nni, dtype=np.float64).ravel())
+    if a.shape[0] < 2:
+        raise ValueError("at least two intervals are needed")
+    lib = L.load()
+    d = torch.from_numpy(a).cuda()
+    wlen = int(lib.mhb_diff_stats_workspace(a.shape[0] - 1))
+    ws = torch.empty(wlen, dtype=torch.float64, device=d.device)
+    out = torch.empty(6, dtype=torch.float64, device=d.device)
+    L.check(lib.mhb_diff_stats_f64(d.data_ptr(), a.shape[0], float(threshold), ws.data_ptr(), wlen, out.data_ptr(),
+                                   _stream_ptr(torch)), "diff_stats")
+    return out.cpu().numpy()
+
+
+def sdnn(nni) -> float:
+    """Standard deviation of the intervals, np.std(nni) (hrv.py:50-63)."""
+    from ..generic import stats
+    return float(stats.std(np.asarray(nni)))
+
+
+def pnnx(nni, unit: str = 'ms', x: float = 50.) -> float:
+    """Proportion of successive differences over ``x`` ms (hrv.py:124-136)."""
+    thr = x * 1e6 / td_factor(unit)
+    r = _diff_stats(nni, thr)
+    return float(r[4] / r[0])
+
+
+def pnn50(nni, unit: str = 'ms') -> float:
+    """Proportion of successive differences over 50 ms (hrv.py:111-121)."""
+    return pnnx(nni, unit, 50.)
+
+
+def rmssd(nni) -> float:
+    """Root mean square of successive differences (hrv.py:139-147)."""
+    return float(np.sqrt(_diff_stats(nni)[5]))
+
+
+def ssd(nni) -> float:
+    """Sum of successive differences (hrv.py:150-158)."""
+    return float(_diff_stats(nni)[1])
+
+
+def sdsd(nni) -> float:
+    """Standard deviation of successive differences (hrv.py:161-170)."""
+    return float(np.sqrt(_diff_stats(nni)[3]))
+
+
+def _segment_index(nni, index, unit, who):
+    if index is None:
+        if unit is None:
+            raise ValueError('%s: index or unit must be specified' % who)
+        index = np.cumsum(np.asarray(nni)) * td_factor(unit)          # hrv.py:42-44, 80-82
+    idx = np.asarray(index)
+    if idx.dtype.kind == "M":
+        idx = idx.astype("datetime64[ns]").view(np.int64)
+    return idx.astype(np.int64)
+
+
+def sdann(nni, index=None, interval: float = 60 * 5, unit=None) -> float:
+    """Standard deviation of the per-segment means of the intervals (segments of ``interval`` seconds over a
+    nanosecond index; hrv.py:66-86).  The reference's version does not compile under current numba (it calls a Python
+    closure from nopython code); this is the computation it states, on the non-uniform window kernels."""
+    from ..util.windows import nonuniform_rolling_apply
+    from ..generic import stats
+    idx = _segment_index(nni, index, unit, "sdann")
+    step = int(interval * 1e9)
+    means = nonuniform_rolling_apply(np.mean)(idx, np.asarray(nni, dtype=np.float64), step, step)
+    return float(stats.std(means))
+
+
+def sdnni(nni, index=None, interval: float = 60 * 5, unit=None) -> float:
+    """Mean of the per-segment standard deviations (hrv.py:89-108); see ``sdann``."""
+    from ..util.windows import nonuniform_rolling_apply
+    from ..generic import stats
+    idx = _segment_index(nni, index, unit, "sdnni")
+    step = int(interval * 1e9)
+    sds = nonuniform_rolling_apply(np.std)(idx, np.asarray(nni, dtype=np.float64), step, step)
+    return float(stats.mean(sds))

@@ -14,7 +14,7 @@ def _dev(a):
     torch = require_cuda()
     if isinstance(a, torch.Tensor):
         return a.to(device="cuda", dtype=torch.float64).contiguous()
-    return torch.from_numpy(np.ascontiguousarray(np.asarray(a, dtype=np.float64))).cuda()
+    return torch.from_numpy(np.array(a, dtype=np.float64, order="C", copy=True)).cuda()
 
 
 def haversine(lat1, lon1, lat2, lon2):

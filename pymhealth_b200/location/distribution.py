@@ -12,6 +12,11 @@ from ..engine import require_cuda, _stream_ptr, window_table, Feature
 _MAX_LABEL_RANGE = 1 << 26
 
 
+def location_variance(df):
+    """DataFrame form of ``arr_location_variance`` (distribution.py:16-25)."""
+    return arr_location_variance(df['latitude'].values, df['longitude'].values)
+
+
 def arr_location_variance(latitude, longitude):
     """var(latitude) + var(longitude), population variances (distribution.py:28-39)."""
     la = np.ascontiguousarray(np.asarray(latitude, dtype=np.float64))

@@ -1,6 +1,6 @@
 """Location distance features -- drop-in for the array forms of ``mhealth.location.features``
-(reference src/mhealth/location/features.py:43-53, 71-84, 98-113).  The pandas DataFrame wrappers of
-that module are glue around these and are out of the hot path."""
+(reference src/mhealth/location/features.py:43-53, 71-84, 98-113).  The pandas DataFrame forms
+(features.py:11-40, 56-68, 87-95) are thin wrappers around them."""
 import ctypes as C
 
 import numpy as np
@@ -9,6 +9,36 @@ from .. import _lib as L
 from ..engine import require_cuda, _stream_ptr
 from . import distance
 from .distance import _dev
+
+
+def determine_home_coords(df, start_time='23:00', end_time='06:00'):
+    """Median latitude / longitude during night-time (features.py:11-24): pandas glue, no kernel involved."""
+    night = df[['latitude', 'longitude']].between_time(start_time, end_time)
+    lat, lon = night.median().values
+    return (lat, lon)
+
+
+def distance_from_home(df, home_coords=None):
+    """DataFrame form of ``arr_distance_from_home`` -> pd.Series 'home_distance' (features.py:27-40)."""
+    from ..util.deps import pd
+    if home_coords is None:
+        home_coords = determine_home_coords(df)
+    out = arr_distance_from_home(df['latitude'].values, df['longitude'].values, home_coords)
+    return pd.Series(out, index=df.index, name='home_distance')
+
+
+def proportion_home_stay(df, limit=0.1, home_coords=None):
+    """DataFrame form of ``arr_proportion_home_stay`` (features.py:56-68)."""
+    if home_coords is None:
+        home_coords = determine_home_coords(df)
+    return arr_proportion_home_stay(df['latitude'].values, df['longitude'].values, limit, home_coords)
+
+
+def successive_distance(df):
+    """DataFrame form of ``arr_successive_distance`` -> pd.Series (features.py:87-95)."""
+    from ..util.deps import pd
+    out = arr_successive_distance(df['latitude'].values, df['longitude'].values)
+    return pd.Series(out, index=df.index, name='latitude')
 
 
 def arr_distance_from_home(latitude, longitude, home_coords):

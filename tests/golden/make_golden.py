@@ -208,8 +208,60 @@ def location_fixture():
     np.savez_compressed(os.path.join(HERE, "ref_location.npz"), **out)
 
 
+def extra_fixture():
+    """Accelerometer pre-stage (inertial/accelerometer.py), HRV time-domain metrics (heart/hrv.py:50-170) and the
+    DataFrame forms of the location features (location/features.py:11-40, 56-68, 87-95)."""
+    import pandas as pd
+    from mhealth.inertial import accelerometer as acc
+    out = {}
+    a = synth.accelerometer(7, 5003)                       # float32 [3, n]
+    out["acc/xyz"] = a
+    out["acc/magnitude_f32"] = acc.magnitude(a[0], a[1], a[2])
+    out["acc/roll_f32"] = acc.roll(a[1], a[2])
+    out["acc/pitch_f32"] = acc.pitch(a[0], a[1], a[2])
+    a64 = a.astype(np.float64)
+    out["acc/magnitude_f64"] = acc.magnitude(a64[0], a64[1], a64[2])
+    out["acc/roll_f64"] = acc.roll(a64[1], a64[2])
+    out["acc/pitch_f64"] = acc.pitch(a64[0], a64[1], a64[2])
+    out["acc/magnitude_dot_f64"] = np.array(acc.magnitude_dot(a64[0], a64[1], a64[2]))
+    out["acc/scalars"] = np.array([acc.magnitude(1.0, 2.0, 2.0), acc.roll(1.0, 1.0), acc.pitch(1.0, 0.0, 1.0)])
+    df = pd.DataFrame({"x": a64[0], "y": a64[1], "z": a64[2]})
+    out["acc/df_magnitude"] = acc.magnitude(df).values
+    out["acc/df_roll"] = acc.roll(df).values
+    out["acc/df_pitch"] = acc.pitch(df).values
+    # RR intervals (ms): 0.8 s +- respiration + noise, a few ectopic jumps
+    rng = np.random.default_rng(4242)
+    n = 4000
+    rr = 800 + 60 * np.sin(np.arange(n) * 0.21) + rng.normal(0, 25, n)
+    rr[rng.integers(0, n, 25)] += rng.normal(0, 150, 25)
+    out["hrv/rr_ms"] = rr
+    out["hrv/sdnn"] = np.array(hrv.sdnn(rr))
+    out["hrv/pnn50"] = np.array(hrv.pnn50(rr, 'ms'))
+    out["hrv/pnnx_20"] = np.array(hrv.pnnx(rr, 'ms', 20.0))
+    out["hrv/pnn50_s"] = np.array(hrv.pnn50(rr / 1e3, 's'))
+    out["hrv/rmssd"] = np.array(hrv.rmssd(rr))
+    out["hrv/ssd"] = np.array(hrv.ssd(rr))
+    out["hrv/sdsd"] = np.array(hrv.sdsd(rr))
+    out["hrv/nni_to_ms"] = hrv.nni_to_ms(rr[:16] * 1e6, 'ns')
+    # location DataFrame forms
+    lat, lon, t, _ = synth.gps(5, 3000)
+    gdf = pd.DataFrame({"latitude": lat, "longitude": lon}, index=pd.to_datetime(t, unit="s"))
+    out["gps/lat"], out["gps/lon"], out["gps/t"] = lat, lon, t
+    home = features.determine_home_coords(gdf)
+    out["gps/home"] = np.array(home)
+    out["gps/distance_from_home"] = np.asarray(features.distance_from_home(gdf))
+    out["gps/proportion_home_stay_0.5"] = np.array(features.proportion_home_stay(gdf, 0.5))
+    # features.successive_distance(df) is NOT recorded: with a datetime index its ``dist[0] = 0`` on a Series appends a
+    # label under pandas 3 (3001 garbage values); the array form is pinned in ref_location.npz instead
+    out["gps/arr_successive_distance"] = features.arr_successive_distance(lat, lon)
+    out["gps/location_variance"] = np.array(distribution.location_variance(gdf))
+    np.savez_compressed(os.path.join(HERE, "ref_extra.npz"), **out)
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["windows", "spectral", "location"]
+    which = sys.argv[1:] or ["windows", "spectral", "location", "extra"]
+    if "extra" in which:
+        extra_fixture()
     if "windows" in which:
         windows_fixture()
     if "spectral" in which:

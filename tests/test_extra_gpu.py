@@ -1,0 +1,107 @@
+"""Accelerometer pre-stage, HRV time-domain metrics and DataFrame front-ends vs fixtures generated from the live
+reference (tests/golden/ref_extra.npz) and the oracle."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ref_extra():
+    return np.load(os.path.join(GOLDEN, "ref_extra.npz"))
+
+
+def test_accelerometer_golden(ref_extra):
+    import pandas as pd
+    from pymhealth_b200.inertial import accelerometer as acc
+    a = ref_extra["acc/xyz"]
+    m = acc.magnitude(a[0], a[1], a[2])
+    assert m.dtype == np.float32
+    np.testing.assert_array_equal(m, ref_extra["acc/magnitude_f32"])            # float32 arithmetic, bit-identical
+    r, p = acc.roll(a[1], a[2]), acc.pitch(a[0], a[1], a[2])
+    assert r.dtype == np.float64 and p.dtype == np.float64
+    # arctan2 in float32 (CUDA atan2f vs libm atan2f: a few float32 ulp), tolerance on degrees
+    np.testing.assert_allclose(r, ref_extra["acc/roll_f32"], rtol=0, atol=180 * 4 * 2.0 ** -23)
+    np.testing.assert_allclose(p, ref_extra["acc/pitch_f32"], rtol=0, atol=180 * 4 * 2.0 ** -23)
+    a64 = a.astype(np.float64)
+    np.testing.assert_array_equal(acc.magnitude(a64[0], a64[1], a64[2]), ref_extra["acc/magnitude_f64"])
+    np.testing.assert_allclose(acc.roll(a64[1], a64[2]), ref_extra["acc/roll_f64"], rtol=1e-14, atol=1e-13)
+    np.testing.assert_allclose(acc.pitch(a64[0], a64[1], a64[2]), ref_extra["acc/pitch_f64"], rtol=1e-14, atol=1e-13)
+    assert acc.magnitude_dot(a64[0], a64[1], a64[2]) == pytest.approx(float(ref_extra["acc/magnitude_dot_f64"]), rel=1e-13)
+    s = ref_extra["acc/scalars"]
+    assert acc.magnitude(1.0, 2.0, 2.0) == s[0]
+    assert acc.roll(1.0, 1.0) == pytest.approx(s[1], rel=1e-15)
+    assert acc.pitch(1.0, 0.0, 1.0) == pytest.approx(s[2], rel=1e-15)
+    df = pd.DataFrame({"x": a64[0], "y": a64[1], "z": a64[2]})
+    got = acc.magnitude(df)
+    assert isinstance(got, pd.Series) and got.name == "magnitude"
+    np.testing.assert_array_equal(got.values, ref_extra["acc/df_magnitude"])
+    np.testing.assert_allclose(acc.roll(df).values, ref_extra["acc/df_roll"], rtol=1e-14, atol=1e-13)
+    np.testing.assert_allclose(acc.pitch(df).values, ref_extra["acc/df_pitch"], rtol=1e-14, atol=1e-13)
+    assert acc.magnitude_dot(df) == pytest.approx(float(ref_extra["acc/magnitude_dot_f64"]), rel=1e-13)
+
+
+@pytest.mark.parametrize("n", [1, 3, 4, 1023, 100003])
+def test_accelerometer_oracle_sizes(n):
+    import torch
+    from oracle import accel as OA
+    from pymhealth_b200.inertial import accelerometer as acc
+    rng = np.random.default_rng(n)
+    x, y, z = (rng.standard_normal(n).astype(np.float32) * 3 for _ in range(3))
+    np.testing.assert_array_equal(acc.magnitude(x, y, z), OA.magnitude(x, y, z))
+    np.testing.assert_allclose(acc.roll(y, z), OA.roll(y, z), rtol=0, atol=180 * 4 * 2.0 ** -23)
+    np.testing.assert_allclose(acc.pitch(x, y, z), OA.pitch(x, y, z), rtol=0, atol=180 * 4 * 2.0 ** -23)
+    # unaligned device views take the scalar kernel; device tensors stay on the device
+    xt = torch.from_numpy(np.concatenate([[0], x]).astype(np.float32)).cuda()[1:]
+    got = acc.magnitude(xt, torch.from_numpy(y).cuda(), torch.from_numpy(z).cuda())
+    assert got.is_cuda
+    np.testing.assert_array_equal(got.cpu().numpy(), OA.magnitude(x, y, z))
+    xi = np.arange(n)
+    assert acc.magnitude(xi, xi, xi).dtype == np.float64       # integers are promoted, as numba does
+    assert acc.magnitude_dot(x, y, z) == pytest.approx(OA.magnitude_dot(x.astype(np.float64), y.astype(np.float64),
+                                                                        z.astype(np.float64)), rel=1e-12)
+
+
+def test_hrv_time_domain_golden(ref_extra):
+    from oracle import hrv as OH
+    from pymhealth_b200.heart import hrv
+    rr = ref_extra["hrv/rr_ms"]
+    assert hrv.sdnn(rr) == pytest.approx(float(ref_extra["hrv/sdnn"]), rel=1e-12)
+    assert hrv.pnn50(rr, 'ms') == float(ref_extra["hrv/pnn50"])                 # counts: exact
+    assert hrv.pnnx(rr, 'ms', 20.0) == float(ref_extra["hrv/pnnx_20"])
+    assert hrv.pnn50(rr / 1e3, 's') == float(ref_extra["hrv/pnn50_s"])
+    assert hrv.rmssd(rr) == pytest.approx(float(ref_extra["hrv/rmssd"]), rel=1e-12)
+    assert hrv.ssd(rr) == pytest.approx(float(ref_extra["hrv/ssd"]), rel=1e-9, abs=1e-9)
+    assert hrv.sdsd(rr) == pytest.approx(float(ref_extra["hrv/sdsd"]), rel=1e-12)
+    np.testing.assert_array_equal(hrv.nni_to_ms(rr[:16] * 1e6, 'ns'), ref_extra["hrv/nni_to_ms"])
+    with pytest.raises(ValueError):
+        hrv.td_factor("h")
+    # segment metrics: the reference's own versions do not compile under numba 0.65 (parity unpinned) -> oracle
+    assert hrv.sdann(rr, unit='ms', interval=120.0) == pytest.approx(OH.sdann(rr, unit='ms', interval=120.0), rel=1e-10)
+    assert hrv.sdnni(rr, unit='ms', interval=120.0) == pytest.approx(OH.sdnni(rr, unit='ms', interval=120.0), rel=1e-10)
+    big = np.random.default_rng(1).normal(800, 50, 300001)
+    assert hrv.rmssd(big) == pytest.approx(OH.rmssd(big), rel=1e-12)
+    assert hrv.pnn50(big) == OH.pnnx(big)
+
+
+def test_location_dataframe_forms(ref_extra):
+    import pandas as pd
+    from pymhealth_b200.location import features, distribution
+    lat, lon, t = ref_extra["gps/lat"], ref_extra["gps/lon"], ref_extra["gps/t"]
+    gdf = pd.DataFrame({"latitude": lat, "longitude": lon}, index=pd.to_datetime(t, unit="s"))
+    home = features.determine_home_coords(gdf)
+    np.testing.assert_array_equal(np.array(home), ref_extra["gps/home"])
+    d = features.distance_from_home(gdf)
+    assert isinstance(d, pd.Series) and d.name == "home_distance" and d.index.equals(gdf.index)
+    np.testing.assert_allclose(d.values, ref_extra["gps/distance_from_home"], rtol=1e-9, atol=1e-12)
+    assert features.proportion_home_stay(gdf, 0.5) == float(ref_extra["gps/proportion_home_stay_0.5"])
+    sd = features.successive_distance(gdf)
+    assert isinstance(sd, pd.Series)
+    # the reference's DataFrame form is broken under pandas 3 (see make_golden.py); the array form is the golden
+    assert sd.index.equals(gdf.index)
+    np.testing.assert_allclose(sd.values, ref_extra["gps/arr_successive_distance"], rtol=1e-9, atol=1e-12)
+    assert distribution.location_variance(gdf) == pytest.approx(float(ref_extra["gps/location_variance"]), rel=1e-10)

@@ -144,3 +144,30 @@ def test_extension_oracle_sanity():
     tab, labels = OX.segment_features(lat, lon, t, np.array([0, 1440, 2880]), np.array([home, home]), 0.1, 0.2, 1800)
     assert tab.shape == (2, len(OX.SEG_COLUMNS))
     assert tab[:, 0].sum() == 2880
+
+
+def test_extra_oracles_pinned():
+    """oracle/accel.py and oracle/hrv.py against fixtures produced by the live reference (ref_extra.npz)."""
+    import os
+    from conftest import GOLDEN
+    from oracle import accel as OA, hrv as OH
+    ref = np.load(os.path.join(GOLDEN, "ref_extra.npz"))
+    a = ref["acc/xyz"]
+    got = OA.magnitude(a[0], a[1], a[2])
+    assert got.dtype == np.float32
+    np.testing.assert_array_equal(got, ref["acc/magnitude_f32"])
+    np.testing.assert_allclose(OA.roll(a[1], a[2]), ref["acc/roll_f32"], rtol=0, atol=180 * 2.0 ** -22)
+    np.testing.assert_allclose(OA.pitch(a[0], a[1], a[2]), ref["acc/pitch_f32"], rtol=0, atol=180 * 2.0 ** -22)
+    a64 = a.astype(np.float64)
+    np.testing.assert_array_equal(OA.magnitude(a64[0], a64[1], a64[2]), ref["acc/magnitude_f64"])
+    np.testing.assert_allclose(OA.roll(a64[1], a64[2]), ref["acc/roll_f64"], rtol=1e-15, atol=1e-13)
+    np.testing.assert_allclose(OA.pitch(a64[0], a64[1], a64[2]), ref["acc/pitch_f64"], rtol=1e-15, atol=1e-13)
+    assert OA.magnitude_dot(a64[0], a64[1], a64[2]) == float(ref["acc/magnitude_dot_f64"])
+    rr = ref["hrv/rr_ms"]
+    assert OH.sdnn(rr) == float(ref["hrv/sdnn"])
+    assert OH.pnnx(rr) == float(ref["hrv/pnn50"])
+    assert OH.pnnx(rr, "ms", 20.0) == float(ref["hrv/pnnx_20"])
+    assert OH.pnnx(rr / 1e3, "s") == float(ref["hrv/pnn50_s"])
+    assert abs(OH.rmssd(rr) - float(ref["hrv/rmssd"])) <= 1e-12 * float(ref["hrv/rmssd"])
+    assert abs(OH.ssd(rr) - float(ref["hrv/ssd"])) <= 1e-9
+    assert abs(OH.sdsd(rr) - float(ref["hrv/sdsd"])) <= 1e-12 * float(ref["hrv/sdsd"])
