@@ -195,6 +195,10 @@ int64_t mhb_diff_stats_workspace(int64_t n_diff);
 int32_t mhb_diff_stats_f64(const double* x, int64_t n, double abs_threshold, double* workspace, int64_t workspace_len,
                            double* out6, void* stream);
 
+/* ppg.slope_sum(x, w) (src/mhealth/heart/ppg.py:28-42): out[i] = sum(diff(x)[i-w : i]) for w <= i < n - 1, else 0;
+ * float64 [n] out whatever the input type. */
+int32_t mhb_slope_sum(int32_t is_f64, const void* x, int64_t n, int32_t w, double* out, void* stream);
+
 /* ---- kernel 3: location traces -------------------------------------------------------------
  * haversine gufuncs, location/distance.py:22-59 (float64 only, like the reference). */
 int32_t mhb_haversine_elementwise(const double* lat1, const double* lon1, const double* lat2,

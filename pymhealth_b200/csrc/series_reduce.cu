@@ -67,8 +67,43 @@ __global__ void diff_final_kernel(const double* __restrict__ x, int64_t nd, cons
     out[5] = m2 / n + mean * mean;     // mean(diff^2)
 }
 
+// ppg.slope_sum (src/mhealth/heart/ppg.py:28-42): out[i] = sum(dx[i-w : i]) for w <= i < n - 1, 0 elsewhere,
+// dx = np.diff(x).  One thread per output sample adds its w differences in index order (float64), so every sample
+// is read from L1/L2 w times but from HBM once; w is ~0.15 s of signal (9 samples at 64 Hz).
+template <typename T>
+__global__ void __launch_bounds__(256) slope_sum_kernel(const T* __restrict__ x, int64_t n, int32_t w,
+                                                        double* __restrict__ out) {
+    const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+        double acc = 0.0;
+        if (i >= w && i < n - 1) {
+            double prev = static_cast<double>(x[i - w]);
+            for (int64_t j = i - w + 1; j <= i; ++j) {
+                const double cur = static_cast<double>(x[j]);
+                acc += cur - prev;
+                prev = cur;
+            }
+        }
+        out[i] = acc;
+    }
+}
+
 }  // namespace
 }  // namespace mhb
+
+extern "C" int32_t mhb_slope_sum(int32_t is_f64, const void* x, int64_t n, int32_t w, double* out, void* stream) {
+    using namespace mhb;
+    MHB_REQUIRE(n >= 0 && w >= 0, MHB_E_ARG, "slope_sum: negative size");
+    if (n == 0) return MHB_OK;
+    MHB_REQUIRE(x && out, MHB_E_ARG, "slope_sum: null pointer");
+    int64_t blocks = (n + 255) / 256;
+    const int64_t cap = static_cast<int64_t>(kNumSMs) * 16;
+    if (blocks > cap) blocks = cap;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (is_f64) slope_sum_kernel<double><<<static_cast<unsigned>(blocks), 256, 0, s>>>(static_cast<const double*>(x), n, w, out);
+    else slope_sum_kernel<float><<<static_cast<unsigned>(blocks), 256, 0, s>>>(static_cast<const float*>(x), n, w, out);
+    return cuda_status(cudaGetLastError(), "slope_sum launch");
+}
 
 extern "C" int64_t mhb_diff_stats_workspace(int64_t n) {
     int64_t blocks = (n + 255) / 256;

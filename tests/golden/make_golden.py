@@ -243,6 +243,11 @@ def extra_fixture():
     out["hrv/ssd"] = np.array(hrv.ssd(rr))
     out["hrv/sdsd"] = np.array(hrv.sdsd(rr))
     out["hrv/nni_to_ms"] = hrv.nni_to_ms(rr[:16] * 1e6, 'ns')
+    from mhealth.heart import ppg as rppg
+    sig = synth.ppg(3, 4000).astype(np.float64)
+    out["ppg/x"] = sig
+    out["ppg/slope_sum_9"] = rppg.slope_sum(sig, 9)
+    out["ppg/slope_sum_1"] = rppg.slope_sum(sig, 1)
     # location DataFrame forms
     lat, lon, t, _ = synth.gps(5, 3000)
     gdf = pd.DataFrame({"latitude": lat, "longitude": lon}, index=pd.to_datetime(t, unit="s"))

@@ -105,3 +105,18 @@ def test_location_dataframe_forms(ref_extra):
     assert sd.index.equals(gdf.index)
     np.testing.assert_allclose(sd.values, ref_extra["gps/arr_successive_distance"], rtol=1e-9, atol=1e-12)
     assert distribution.location_variance(gdf) == pytest.approx(float(ref_extra["gps/location_variance"]), rel=1e-10)
+
+
+def test_ppg_slope_sum(ref_extra):
+    from pymhealth_b200.heart import ppg
+    x = ref_extra["ppg/x"]
+    for w in (9, 1):
+        got = ppg.slope_sum(x, w)
+        want = ref_extra["ppg/slope_sum_%d" % w]
+        assert got.dtype == np.float64 and got.shape == want.shape
+        np.testing.assert_allclose(got, want, rtol=0, atol=1e-13 * np.abs(x).max())
+        assert np.all(got[:w] == 0) and got[-1] == 0
+    got32 = ppg.slope_sum(x.astype(np.float32), 9)                 # float32 samples, float64 sums
+    np.testing.assert_allclose(got32, ref_extra["ppg/slope_sum_9"], rtol=0, atol=1e-6 * np.abs(x).max())
+    assert ppg.slope_sum(np.zeros(0), 3).shape == (0,)
+    assert np.all(ppg.slope_sum(np.arange(5.0), 9) == 0)           # window longer than the signal
