@@ -21,6 +21,8 @@
 //           about half a CTA's worth of windows is pending so it is not a one-warp bubble.
 // Parity notes (SURVEY section 8c gotchas): population variance; kurtosis / skewness return 0 for a
 // constant window; zero is "not positive" for crossings; no partial tail window.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace mhb {
@@ -582,9 +584,16 @@ struct CellChoice {
 
 CellChoice choose_cell(int64_t g, bool allow_vec4) {
     CellChoice c;
+    if (allow_vec4 && g % 16 == 0 && getenv("MHB_STATS_CELL8") == nullptr) {
+        // power-of-two-ish blocks have no odd divisor: 4 x 128-bit loads per thread.  Lane stride 64 B gives a 4-way
+        // conflict on LDS.128 (16 wavefronts per warp load, 512 samples per 64 cycles: far above the 4 B/sample HBM
+        // can feed), and a 16-sample cell halves the per-stage overhead per sample of the 8-sample one.
+        c.m = 16;
+        c.mcell_template = -16;
+        return c;
+    }
     if (allow_vec4 && g % 8 == 0) {
-        // power-of-two-ish blocks have no odd divisor: 2 x 128-bit loads per thread (lane stride 32 B:
-        // 2-way conflict on LDS.128, harmless at 4 B/sample of demand)
+        // 2 x 128-bit loads per thread (lane stride 32 B: 2-way conflict on LDS.128)
         c.m = 8;
         c.mcell_template = -8;
         return c;
@@ -618,6 +627,9 @@ cudaError_t launch_with_cell(const StatsPlan& P, int mt, dim3 grid, size_t smem,
     }
     if (mt == -8) {
         if constexpr (sizeof(InT) == 4) MHB_LAUNCH(-8, 0)
+    }
+    if (mt == -16) {
+        if constexpr (sizeof(InT) == 4) MHB_LAUNCH(-16, 0)
     }
     if (mt == 25) {
         if (P.cpb == 10 && P.k == 2 && P.hop == 1 && P.TB == 25) MHB_LAUNCH(25, 1)
