@@ -43,11 +43,10 @@ constexpr int kThreadsF = 224;           // 14 half-warps
 constexpr int kNA = 10;                  // pass-A threads per window (n2)
 constexpr int kNP = 13;                  // pass-B threads per window (p = 0..12)
 constexpr int kWSB = 251;                // complex stride between windows in buf (odd: conflict free)
+constexpr int kRowStride = 253;          // float stride between PSD rows (odd: conflict free)
 constexpr int kMaxColsF = 32;
-constexpr int kMaxSum = 6;               // distinct band ranges per call
-constexpr int kMaxArg = 4;               // distinct arg-max ranges per call
 constexpr int kTileElems = ((kBW - 1) * kS + kW + 3 + 4) & ~3;     // 4256 floats
-constexpr int kMeanParts = 7;
+static_assert(2 * kBW + kBW * kRowStride <= kTileElems, "PSD rows + DC cells must fit a consumed tile slot");
 
 struct FastPlan {
     const float* x;
@@ -57,11 +56,9 @@ struct FastPlan {
     void* out;
     int32_t out_f32;
     int64_t o_series, o_window, o_col;
-    int32_t n_cols, n_sum, n_arg;
+    int32_t n_cols;
     int32_t col[kMaxColsF];              // MHB_S_* kind
-    int32_t cref[kMaxColsF];             // index into the sum / arg range tables
-    int32_t sum_lo[kMaxSum], sum_hi[kMaxSum];
-    int32_t arg_lo[kMaxArg], arg_hi[kMaxArg];
+    int32_t lo[kMaxColsF], hi[kMaxColsF];   // bin range [lo, hi) of the column
     int32_t use_tma;
 };
 
@@ -129,36 +126,118 @@ __device__ __forceinline__ void dft_composite(C* a) {
 __device__ __forceinline__ void dft10(C* a) { dft_composite<10, 2, 5>(a); }
 __device__ __forceinline__ void dft25(C* a) { dft_composite<25, 5, 5>(a); }
 
-// shared-memory layout of the reduction scratch that overlays the consumed tile slot
-struct Scratch {
-    float* ptot;      // [BW][NP]  sum of the thread's bins (bin 0 excluded)
-    float* ph;        // [BW][NP]  entropy partial (natural log units)
-    float* psum;      // [kMaxSum][BW][NP]
-    float* pbest;     // [kMaxArg][BW][NP]
-    int* parg;        // [kMaxArg][BW][NP]
-    double* dc;       // [BW]     exact bin 0
-    __device__ __forceinline__ void carve(float* base) {
-        constexpr int Q = kBW * kNP;
-        dc = reinterpret_cast<double*>(base);
-        float* p = base + 2 * kBW;
-        ptot = p; p += Q;
-        ph = p; p += Q;
-        psum = p; p += kMaxSum * Q;
-        pbest = p; p += kMaxArg * Q;
-        parg = reinterpret_cast<int*>(p);
-    }
-};
-static_assert(2 * kBW + (2 + kMaxSum + 2 * kMaxArg) * kBW * kNP <= kTileElems, "scratch must fit a tile slot");
+// sum over the 4 lanes of a quad, fixed order (result in every lane)
+__device__ __forceinline__ float quad_sum(float v) {
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    v += __shfl_xor_sync(0xffffffffu, v, 2);
+    return v;
+}
 
-// bit k2 of the mask: bin (lowset ? p + 25 k2 : 250 - p - 25 k2) lies in [lo, hi)
-__device__ __forceinline__ uint32_t range_mask(int p, bool lowset, int lo, int hi) {
-    uint32_t m = 0;
+// Deferred PSD reducers of one finished batch: 4 lanes (a quad) per window.  Totals and the entropy come from the 13
+// per-thread records pass B left behind (sum, sum y log2 y, exponent); band sums and arg-max read only the bins of
+// their range from the window's PSD row in shared memory.  Runs on the two warps that have no pass-A work while the
+// other five transform the next batch.
+struct Records {
+    const float* ptot;   // [BW][NP]  sum of the thread's bins (bin 0 excluded)
+    const float* ph;     // [BW][NP]  sum y log2 y over the thread's bins, y = psd 2^-pe
+    const int* pe;       // [BW][NP]  binary exponent of the thread's ptot
+};
+
+__device__ __forceinline__ void reduce_rows(const FastPlan& P, const float* __restrict__ slot_base, const Records R,
+                                            int t /*0..63*/, uint32_t series, int64_t w0, int nwin) {
+    const int w = t >> 2, j = t & 3;
+    const bool act = w < nwin;
+    const int wc = act ? w : 0;                       // idle quads alias window 0: they never store
+    const double* dcs = reinterpret_cast<const double*>(slot_base);
+    const float* prow = slot_base + 2 * kBW + wc * kRowStride;      // prow[k] = |X[k]|^2, k = 1..250
+    const double dc = dcs[wc];
+    const int q0 = wc * kNP;
+    // lane j of the quad folds records j, j + 4, j + 8 (, 12); quad sums in a fixed order: every lane gets the same bits
+    float r0 = R.ptot[q0 + j], r1 = R.ptot[q0 + j + 4], r2 = R.ptot[q0 + j + 8], r3 = j == 0 ? R.ptot[q0 + 12] : 0.f;
+    double rest = (static_cast<double>(r0) + static_cast<double>(r1)) + (static_cast<double>(r2) + static_cast<double>(r3));
+    rest += __shfl_xor_sync(0xffffffffu, rest, 1);
+    rest += __shfl_xor_sync(0xffffffffu, rest, 2);       // all bins but 0
+    const double total = rest + dc;
+    // Entropy (information.py:10-20): H = -p0 ln p0 - sum_{k>=1} p_k ln p_k.  With E = binary exponent of the total
+    // and f = total 2^-E in [1, 2):
+    //   -(sum_{k>=1} p_k log2 p_k) f = (rest 2^-E) log2 f + sum_t [ tot_t 2^-E (E - e_t) - S_t 2^(e_t - E) ]
+    // every term is O(1), so a float log2 of f (absolute error 2^-22) and a float64 sum of float records suffice.
+    const float tf = static_cast<float>(total);
+    const int E = ((__float_as_int(tf) >> 23) & 0xff) - 127;
+    const float down = __int_as_float((127 - E) << 23);              // 2^-E
+    double acc = 0.0;
 #pragma unroll
-    for (int k2 = 0; k2 < 10; ++k2) {
-        const int k = lowset ? p + 25 * k2 : kN - p - 25 * k2;
-        if (k >= lo && k < hi) m |= 1u << k2;
+    for (int i = 0; i < 4; ++i) {
+        const int idx = j + 4 * i;
+        if (idx < kNP) {
+            const int e = R.pe[q0 + idx];
+            const int de = E - e;
+            const float u = R.ptot[q0 + idx] * down;
+            const float rel = de < 60 ? __int_as_float((127 - de) << 23) : 0.f;      // 2^(e - E)
+            acc += static_cast<double>(u) * static_cast<double>(de) - static_cast<double>(R.ph[q0 + idx] * rel);
+        }
     }
-    return m;
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+    const float f = tf * down;
+    const float hrest2 = static_cast<float>(rest * static_cast<double>(down) * static_cast<double>(__log2f(f)) + acc) *
+                         __fdividef(1.0f, f);
+    const float inv_t = __fdividef(1.0f, tf);
+    const float p0 = static_cast<float>(dc) * inv_t, qrest = static_cast<float>(rest) * inv_t;
+    const float h0 = p0 > 0.f ? -p0 * (qrest < 0.5f ? log1pf(-qrest) : __logf(p0)) : 0.f;   // DC term, log1p near p0 = 1
+    const float h = fmaf(0.69314718055994530942f, hrest2, h0);
+#pragma unroll 1
+    for (int c = 0; c < P.n_cols; ++c) {
+        const int kind = P.col[c];
+        const int lo = P.lo[c], hi = P.hi[c];
+        double v;
+        if (kind == MHB_S_TOTAL_POWER) {
+            v = total;
+        } else if (kind == MHB_S_ENTROPY) {
+            v = total > 0.0 ? static_cast<double>(h) : CUDART_NAN;
+        } else if (kind == MHB_S_BAND_POWER || kind == MHB_S_REL_BAND_POWER) {
+            float acc = 0.f;
+#pragma unroll 4
+            for (int k = (lo > 1 ? lo : 1) + j; k < hi; k += 4) acc += prow[k];
+            double bsum = static_cast<double>(quad_sum(acc));
+            if (lo <= 0 && hi > 0) bsum += dc;
+            v = kind == MHB_S_BAND_POWER ? bsum : bsum / total;
+        } else {                                      // peak frequency / bin: first maximum in [lo, hi)
+            float best = -1.f;
+            int arg = 0x7fffffff;
+#pragma unroll 4
+            for (int k = (lo > 1 ? lo : 1) + j; k < hi; k += 4) {
+                const float pv = prow[k];
+                if (pv > best) {
+                    best = pv;
+                    arg = k;
+                }
+            }
+            if (j == 0 && lo <= 0 && hi > 0) {        // bin 0 competes too; ties go to the lower bin
+                const float d = static_cast<float>(dc);
+                if (d >= best) {
+                    best = d;
+                    arg = 0;
+                }
+            }
+#pragma unroll
+            for (int o = 1; o <= 2; o <<= 1) {
+                const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+                const int oa = __shfl_xor_sync(0xffffffffu, arg, o);
+                if (ob > best || (ob == best && oa < arg)) {
+                    best = ob;
+                    arg = oa;
+                }
+            }
+            if (arg == 0x7fffffff) v = CUDART_NAN;
+            else v = kind == MHB_S_PEAK_BIN ? static_cast<double>(arg) : static_cast<double>(arg) * P.bin_hz;
+        }
+        if (act && j == (c & 3)) {                    // the four lanes of the quad share the stores
+            const int64_t o = static_cast<int64_t>(series) * P.o_series + (w0 + w) * P.o_window + c * P.o_col;
+            if (P.out_f32) reinterpret_cast<float*>(P.out)[o] = static_cast<float>(v);
+            else reinterpret_cast<double*>(P.out)[o] = v;
+        }
+    }
 }
 
 __global__ void __launch_bounds__(kThreadsF, 3) spectral_fast_kernel(const FastPlan P) {
@@ -168,32 +247,26 @@ __global__ void __launch_bounds__(kThreadsF, 3) spectral_fast_kernel(const FastP
     C* buf = reinterpret_cast<C*>(tiles + 2 * kTileElems);                  // BW x kWSB complex
     C* twA = buf + kBW * kWSB;                                              // [25][10]  w250^(n2 k1)
     C* twB = twA + 25 * kNA;                                                // [10][13]  w500^(p + 25 k2)
-    float* msum = reinterpret_cast<float*>(twB + 10 * kNP);                 // [kMeanParts][BW]
-    float* piv = msum + kMeanParts * kBW;                                   // [BW] pivot (mean estimate) per window
-    uint32_t* masks = reinterpret_cast<uint32_t*>(piv + kBW);               // [kMaxSum + kMaxArg][2][16]
+    float* piv = reinterpret_cast<float*>(twB + 10 * kNP);                  // [BW] pivot (mean estimate) per window
+    float* rec_tot = piv + kBW;                                             // [BW][NP] pass-B records (see Records)
+    float* rec_h = rec_tot + kBW * kNP;
+    int* rec_e = reinterpret_cast<int*>(rec_h + kBW * kNP);
+    const Records R = {rec_tot, rec_h, rec_e};
     const int tid = threadIdx.x;
-    const int w = tid & 15;              // window of the batch this thread works for (all phases)
+    const int w = tid & 15;              // window of the batch this thread transforms
     const int role = tid >> 4;           // half-warp index 0..13
 
     for (int i = tid; i < 25 * kNA; i += kThreadsF) {
         const int k1 = i / kNA, n2 = i - k1 * kNA;
-        double s, c;
-        sincospi(-2.0 * static_cast<double>(k1 * n2) / 250.0, &s, &c);
-        twA[i] = {static_cast<float>(c), static_cast<float>(s)};
+        double sn, cs;
+        sincospi(-2.0 * static_cast<double>(k1 * n2) / 250.0, &sn, &cs);
+        twA[i] = {static_cast<float>(cs), static_cast<float>(sn)};
     }
     for (int i = tid; i < 10 * kNP; i += kThreadsF) {
         const int k2 = i / kNP, p = i - k2 * kNP;
-        double s, c;
-        sincospi(-2.0 * static_cast<double>(p + 25 * k2) / 500.0, &s, &c);
-        twB[i] = {static_cast<float>(c), static_cast<float>(s)};
-    }
-    for (int i = tid; i < (kMaxSum + kMaxArg) * 2 * 16; i += kThreadsF) {
-        const int r = i >> 5, lowset = (i >> 4) & 1, p = i & 15;
-        const bool is_sum = r < kMaxSum;
-        const int ri = is_sum ? r : r - kMaxSum;
-        const bool live = is_sum ? ri < P.n_sum : ri < P.n_arg;
-        const int lo = is_sum ? P.sum_lo[ri] : P.arg_lo[ri], hi = is_sum ? P.sum_hi[ri] : P.arg_hi[ri];
-        masks[i] = (live && p < kNP) ? range_mask(p, lowset != 0, lo, hi) : 0u;
+        double sn, cs;
+        sincospi(-2.0 * static_cast<double>(p + 25 * k2) / 500.0, &sn, &cs);
+        twB[i] = {static_cast<float>(cs), static_cast<float>(sn)};
     }
     if (tid == 0) {
         mbar_init(&full[0], 1);
@@ -202,24 +275,33 @@ __global__ void __launch_bounds__(kThreadsF, 3) spectral_fast_kernel(const FastP
     }
     __syncthreads();
 
-    auto batch_geom = [&](int64_t b, int64_t& series, int64_t& w0, int& nwin, int64_t& goff, int& n_valid) {
-        const uint32_t bps = static_cast<uint32_t>(P.batches_per_series);      // host guarantees < 2^31 batches
-        const uint32_t sr = static_cast<uint32_t>(b) / bps;
-        const uint32_t bi = static_cast<uint32_t>(b) - sr * bps;
-        series = sr;
-        w0 = static_cast<int64_t>(bi) * kBW;
+    // batch b = (series, bi): advanced incrementally (no division in the loop)
+    const uint32_t bps = static_cast<uint32_t>(P.batches_per_series);          // host guarantees < 2^31 batches
+    uint32_t series = static_cast<uint32_t>(blockIdx.x) / bps;
+    uint32_t bi = static_cast<uint32_t>(blockIdx.x) - series * bps;
+    const uint32_t step_s = gridDim.x / bps, step_b = gridDim.x - step_s * bps;
+    auto geom_of = [&](uint32_t sr, uint32_t bix, int64_t& w0, int& nwin, int64_t& goff, int& n_valid) {
+        w0 = static_cast<int64_t>(bix) * kBW;
         const int64_t left = P.nw - w0;
         nwin = left < kBW ? static_cast<int>(left) : kBW;
-        goff = series * P.series_stride + w0 * kS;
+        goff = static_cast<int64_t>(sr) * P.series_stride + w0 * kS;
         n_valid = (nwin - 1) * kS + kW;
+    };
+    auto advance = [&](uint32_t& sr, uint32_t& bix) {
+        sr += step_s;
+        bix += step_b;
+        if (bix >= bps) {
+            bix -= bps;
+            ++sr;
+        }
     };
     auto tma_ok = [&](int64_t goff, int n_load) {
         return P.use_tma && (goff % 4 == 0) && (goff + n_load <= P.total_elems);
     };
-    auto issue = [&](int64_t b, int slot) {              // thread 0 only
-        int64_t series, w0, goff;
+    auto issue = [&](uint32_t sr, uint32_t bix, int slot) {              // thread 0 only
+        int64_t w0, goff;
         int nwin, n_valid;
-        batch_geom(b, series, w0, nwin, goff, n_valid);
+        geom_of(sr, bix, w0, nwin, goff, n_valid);
         const int n_load = (n_valid + 3) & ~3;
         if (tma_ok(goff, n_load)) {
             fence_proxy_async();                          // earlier generic-proxy accesses of the slot are done
@@ -230,17 +312,22 @@ __global__ void __launch_bounds__(kThreadsF, 3) spectral_fast_kernel(const FastP
 
     int slot = 0;
     uint32_t parity0 = 0, parity1 = 0;
-    int64_t b = blockIdx.x;
+    const uint32_t n_series = static_cast<uint32_t>(P.total_batches / bps);
     if (tid == 0) {
-        if (b < P.total_batches) issue(b, 0);
-        if (b + gridDim.x < P.total_batches) issue(b + gridDim.x, 1);
+        if (series < n_series) issue(series, bi, 0);
+        uint32_t s2 = series, b2 = bi;
+        advance(s2, b2);
+        if (s2 < n_series) issue(s2, b2, 1);
     }
     bool first = true;
+    uint32_t prev_series = 0;            // the batch whose PSD rows wait in the other slot
+    int64_t prev_w0 = 0;
+    int prev_nwin = 0;
 
-    for (; b < P.total_batches; b += gridDim.x) {
-        int64_t series, w0, goff;
+    for (; series < n_series; advance(series, bi)) {
+        int64_t w0, goff;
         int nwin, n_valid;
-        batch_geom(b, series, w0, nwin, goff, n_valid);
+        geom_of(series, bi, w0, nwin, goff, n_valid);
         float* tile = tiles + slot * kTileElems;
         const int n_load = (n_valid + 3) & ~3;
         if (tma_ok(goff, n_load)) {
@@ -252,88 +339,78 @@ __global__ void __launch_bounds__(kThreadsF, 3) spectral_fast_kernel(const FastP
                 parity1 ^= 1;
             }
         } else {
-            // unaligned base or the last few samples of the buffer: guarded cooperative copy.  The slot's previous
-            // readers (the finalize phase two batches ago) are behind at least one barrier of the last iteration.
+            // unaligned base or the last few samples of the buffer: guarded cooperative copy.  The slot held the PSD
+            // rows of the batch before the previous one; they were reduced before the barriers of the last iteration.
             for (int i = tid; i < n_valid; i += kThreadsF) tile[i] = P.x[goff + i];
             __syncthreads();
         }
         const bool act = w < nwin;
 
-        // ---- window mean estimate (pivot of the transform): 14 threads per window, every other float2
-        {
-            float sm = 0.f;
+        if (role < kNA) {
+            // ---- pass A (warps 0-4): 25-point DFTs of the stride-10 subsequences, inter-pass twiddle, exchange
             if (act) {
-                const float2* z = reinterpret_cast<const float2*>(tile + w * kS) + role * 18;
-                const int cnt = role == 13 ? 8 : 9;       // float2 pairs [36 role, 36 role + 36) within 250
+                const int n2 = role;
+                // pivot of the transform: a 16-sample estimate of the window mean (any value near the mean works:
+                // bin 0 is restored exactly in pass B; the pivot only keeps a large DC out of the float32 dynamic
+                // range).  Every thread of the window reads the same 16 samples, so they agree bit for bit.
+                const float* xw = tile + w * kS;
+                float m = 0.f;
 #pragma unroll
-                for (int i = 0; i < 9; ++i)
-                    if (i < cnt) {
-                        const float2 v = z[2 * i];
-                        sm += v.x + v.y;
-                    }
+                for (int j = 0; j < 16; ++j) m += xw[15 + 31 * j];
+                m *= (1.0f / 16.0f);
+                const float mh = -0.5f * m;
+                const float2* z = reinterpret_cast<const float2*>(xw) + n2;
+                C a[25];
+#pragma unroll
+                for (int n1 = 0; n1 < 25; ++n1) {
+                    const float2 v = z[kNA * n1];
+                    a[n1] = {fmaf(v.x, 0.5f, mh), fmaf(v.y, 0.5f, mh)};
+                }
+                dft25(a);
+                C* dst = buf + w * kWSB + n2 * 25;
+                dst[0] = a[0];
+                if (n2 == 0) {
+#pragma unroll
+                    for (int k1 = 1; k1 < 25; ++k1) dst[k1] = a[k1];
+                    piv[w] = m;
+                } else {
+                    const C* tw = twA + n2;
+#pragma unroll
+                    for (int k1 = 1; k1 < 25; ++k1) dst[k1] = cmul(a[k1], tw[k1 * kNA]);
+                }
             }
-            sm += __shfl_xor_sync(0xffffffffu, sm, 16);    // roles 2j and 2j + 1 share a warp
-            if ((role & 1) == 0) msum[(role >> 1) * kBW + w] = sm;
+        } else if (!first) {
+            // ---- warps 5-6: PSD reducers of the PREVIOUS batch, whose rows sit in the other (consumed) tile slot
+            reduce_rows(P, tiles + (slot ^ 1) * kTileElems, R, tid - kNA * 16, prev_series, prev_w0, prev_nwin);
         }
-        __syncthreads();                                   // (B1) also: everyone finished the previous batch
-        // refill the slot the previous batch used (its reduction scratch is dead now)
+        __syncthreads();                                   // (B1) pass A done, previous batch fully reduced
+        // refill the slot the previous batch used (its PSD rows are dead now)
         if (tid == 0 && !first) {
-            const int64_t bn = b + gridDim.x;
-            if (bn < P.total_batches) issue(bn, slot ^ 1);
+            uint32_t s2 = series, b2 = bi;
+            advance(s2, b2);
+            if (s2 < n_series) issue(s2, b2, slot ^ 1);
         }
         first = false;
 
-        // ---- pass A: 25-point DFTs of the stride-10 subsequences, inter-pass twiddle, exchange
-        if (role < kNA && act) {
-            const int n2 = role;
-            float m = 0.f;
-#pragma unroll
-            for (int j = 0; j < kMeanParts; ++j) m += msum[j * kBW + w];
-            m *= (1.0f / 250.0f);                          // 250 of the 500 samples were summed
-            const float mh = -0.5f * m;
-            const float2* z = reinterpret_cast<const float2*>(tile + w * kS) + n2;
-            C a[25];
-#pragma unroll
-            for (int n1 = 0; n1 < 25; ++n1) {
-                const float2 v = z[kNA * n1];
-                a[n1] = {fmaf(v.x, 0.5f, mh), fmaf(v.y, 0.5f, mh)};
-            }
-            dft25(a);
-            C* dst = buf + w * kWSB + n2 * 25;
-            dst[0] = a[0];
-            if (n2 == 0) {
-#pragma unroll
-                for (int k1 = 1; k1 < 25; ++k1) dst[k1] = a[k1];
-            } else {
-                const C* tw = twA + n2;
-#pragma unroll
-                for (int k1 = 1; k1 < 25; ++k1) dst[k1] = cmul(a[k1], tw[k1 * kNA]);
-            }
-            if (n2 == 0) piv[w] = m;
-        }
-        __syncthreads();                                   // (B2)
-
-        // ---- pass B phase 1: 10-point DFTs -> untangle -> |X|^2 in registers -> partial reductions
-        Scratch sc;
-        sc.carve(tile);                                    // the tile was consumed by pass A
-        float psd_l[10], psd_h[10];                        // p >= 1: bins p + 25 k2 / 250 - p - 25 k2
+        // ---- pass B: 10-point DFTs -> untangle -> |X|^2 -> PSD row in the consumed tile slot
         const bool has_b = role < kNP - 1;                 // p = role + 1 = 1..12
         const bool has_0 = role == kNP - 1;                // p = 0 lives alone in the lower half of warp 6
-        const int p = has_b ? role + 1 : 0;
-        float pivot = 0.f;
         if ((has_b || has_0) && act) {
+            const int p = has_b ? role + 1 : 0;
             const C* bw = buf + w * kWSB;
-            pivot = piv[w];
+            float* prow = tile + 2 * kBW + w * kRowStride;
             C A[10];
 #pragma unroll
             for (int n2 = 0; n2 < 10; ++n2) A[n2] = bw[n2 * 25 + p];
             dft10(A);                                      // A[k2] = Z[p + 25 k2] / 2
-            float tot = 0.f;
+            float psd[20];                                 // this thread's bins (unused slots stay 0)
             if (has_b) {
                 C B[10];
 #pragma unroll
                 for (int n2 = 0; n2 < 10; ++n2) B[n2] = bw[n2 * 25 + 25 - p];
                 dft10(B);                                  // B[k2] = Z[25 - p + 25 k2] / 2
+                float* lo_ptr = prow + p;                  // bin p + 25 k2
+                float* hi_ptr = prow + kN - p;             // bin 250 - p - 25 k2
 #pragma unroll
                 for (int k2 = 0; k2 < 10; ++k2) {
                     const C zk = A[k2], zn = B[9 - k2];   // (k, N - k), k = p + 25 k2
@@ -341,15 +418,16 @@ __global__ void __launch_bounds__(kThreadsF, 3) spectral_fast_kernel(const FastP
                     const C e = {zk.x + zn.x, zk.y - zn.y};
                     const C o = {zk.y + zn.y, zn.x - zk.x};
                     const C t = cmul(o, t2);
-                    const float ar = e.x + t.x, ai = e.y + t.y, br = e.x - t.x, bi = e.y - t.y;
-                    psd_l[k2] = fmaf(ar, ar, ai * ai);
-                    psd_h[k2] = fmaf(br, br, bi * bi);
-                    tot += psd_l[k2] + psd_h[k2];
+                    const float ar = e.x + t.x, ai = e.y + t.y, br = e.x - t.x, bi2 = e.y - t.y;
+                    psd[2 * k2] = fmaf(ar, ar, ai * ai);
+                    psd[2 * k2 + 1] = fmaf(br, br, bi2 * bi2);
+                    lo_ptr[25 * k2] = psd[2 * k2];
+                    hi_ptr[-25 * k2] = psd[2 * k2 + 1];
                 }
             } else {
                 // p = 0: Z[25 k2]; pairs (k2, 10 - k2) for k2 = 1..4, the self pair k2 = 5, and bins 0 / N from Z[0]
 #pragma unroll
-                for (int k2 = 0; k2 < 10; ++k2) psd_l[k2] = psd_h[k2] = 0.f;
+                for (int i = 0; i < 20; ++i) psd[i] = 0.f;
 #pragma unroll
                 for (int k2 = 1; k2 <= 5; ++k2) {
                     const C zk = A[k2], zn = A[10 - k2];
@@ -357,152 +435,58 @@ __global__ void __launch_bounds__(kThreadsF, 3) spectral_fast_kernel(const FastP
                     const C e = {zk.x + zn.x, zk.y - zn.y};
                     const C o = {zk.y + zn.y, zn.x - zk.x};
                     const C t = cmul(o, t2);
-                    const float ar = e.x + t.x, ai = e.y + t.y, br = e.x - t.x, bi = e.y - t.y;
-                    psd_l[k2] = fmaf(ar, ar, ai * ai);                    // bin 25 k2
-                    if (k2 < 5) psd_h[k2] = fmaf(br, br, bi * bi);        // bin 250 - 25 k2
-                    tot += psd_l[k2] + psd_h[k2];
+                    const float ar = e.x + t.x, ai = e.y + t.y, br = e.x - t.x, bi2 = e.y - t.y;
+                    psd[2 * k2] = fmaf(ar, ar, ai * ai);
+                    prow[25 * k2] = psd[2 * k2];                                // bin 25 k2
+                    if (k2 < 5) {
+                        psd[2 * k2 + 1] = fmaf(br, br, bi2 * bi2);
+                        prow[kN - 25 * k2] = psd[2 * k2 + 1];                   // bin 250 - 25 k2
+                    }
                 }
                 const float xn = 2.f * (A[0].x - A[0].y);
-                psd_h[0] = xn * xn;                                       // bin N = 250 (Nyquist)
-                tot += psd_h[0];
+                psd[0] = xn * xn;
+                prow[kN] = psd[0];                                              // bin N = 250 (Nyquist)
                 const double x0 = 2.0 * (static_cast<double>(A[0].x) + static_cast<double>(A[0].y)) +
-                                  static_cast<double>(kW) * static_cast<double>(pivot);
-                sc.dc[w] = x0 * x0;                                       // exact DC: FFT(x - m)[0] + W m
+                                  static_cast<double>(kW) * static_cast<double>(piv[w]);
+                reinterpret_cast<double*>(tile)[w] = x0 * x0;                   // exact DC: FFT(x - m)[0] + W m
+            }
+            // records for the deferred reducers: total of the thread's bins, and the entropy partial in ONE pass: with
+            // y = psd 2^-e (e = binary exponent of this thread's total -- an exact scaling that keeps |log2 y| small for
+            // the bins that matter)  sum psd log2 psd = 2^e sum y log2 y + e tot
+            float ta = 0.f, tb = 0.f;
+#pragma unroll
+            for (int i = 0; i < 20; i += 2) {
+                ta += psd[i];
+                tb += psd[i + 1];
+            }
+            const float tot = ta + tb;
+            const int eb = (__float_as_int(tot) >> 23) & 0xff;
+            const float scale = __int_as_float((254 - eb) << 23);               // 2^-(eb - 127)
+            float ha = 0.f, hb = 0.f;
+#pragma unroll
+            for (int i = 0; i < 20; i += 2) {
+                const float y1 = psd[i] * scale, y2 = psd[i + 1] * scale;
+                ha = fmaf(y1, __log2f(fmaxf(y1, 1e-37f)), ha);
+                hb = fmaf(y2, __log2f(fmaxf(y2, 1e-37f)), hb);
             }
             const int q = w * kNP + p;
-            sc.ptot[q] = tot;
-            // band sums over the thread's bins (bin 0 is added by the finalize step from sc.dc)
-#pragma unroll 1
-            for (int r = 0; r < P.n_sum; ++r) {
-                const uint32_t ml = masks[(r * 2 + 1) * 16 + p], mh2 = masks[(r * 2) * 16 + p];
-                float acc = 0.f;
-#pragma unroll
-                for (int k2 = 0; k2 < 10; ++k2) {
-                    if (ml & (1u << k2)) acc += psd_l[k2];
-                    if (mh2 & (1u << k2)) acc += psd_h[k2];
-                }
-                sc.psum[r * kBW * kNP + q] = acc;
-            }
-            // first maximum over the thread's bins, visited in ascending bin order:
-            //   p, 25 - p, p + 25, 50 - p, ...   (low set k2 = i, high set k2 = 9 - i)
-#pragma unroll 1
-            for (int r = 0; r < P.n_arg; ++r) {
-                const uint32_t ml = masks[((kMaxSum + r) * 2 + 1) * 16 + p], mh2 = masks[((kMaxSum + r) * 2) * 16 + p];
-                float best = -1.f;
-                int arg = 0x7fffffff;
-#pragma unroll
-                for (int i = 0; i < 10; ++i) {
-                    if (has_b || i > 0) {                                 // p = 0: bin 0 is handled by the finalize step
-                        if ((ml & (1u << i)) && psd_l[i] > best) {
-                            best = psd_l[i];
-                            arg = p + 25 * i;
-                        }
-                    }
-                    if ((mh2 & (1u << (9 - i))) && psd_h[9 - i] > best) {
-                        best = psd_h[9 - i];
-                        arg = kN - p - 25 * (9 - i);
-                    }
-                }
-                sc.pbest[r * kBW * kNP + q] = best;
-                sc.parg[r * kBW * kNP + q] = arg;
-            }
+            rec_tot[q] = tot;
+            rec_h[q] = ha + hb;
+            rec_e[q] = eb - 127;
         }
-        __syncthreads();                                   // (B3)
-
-        // ---- pass B phase 2: entropy of the normalised PSD from the register values
-        if ((has_b || has_0) && act) {
-            float rest = 0.f;
-#pragma unroll
-            for (int j = 0; j < kNP; ++j) rest += sc.ptot[w * kNP + j];
-            const double dc = sc.dc[w];
-            const float total = rest + static_cast<float>(dc);
-            const float inv = __fdividef(1.0f, total);
-            float h = 0.f;                                  // sum q log2 q
-#pragma unroll
-            for (int k2 = 0; k2 < 10; ++k2) {
-                if (has_b || (k2 >= 1 && k2 <= 5)) {
-                    const float q1 = fmaf(psd_l[k2], inv, 1e-30f);
-                    h = fmaf(q1, __log2f(q1), h);
-                }
-                if (has_b || k2 <= 4) {                      // p = 0: bins 250 - 25 k2 (k2 = 1..4) and the Nyquist bin
-                    const float q2 = fmaf(psd_h[k2], inv, 1e-30f);
-                    h = fmaf(q2, __log2f(q2), h);
-                }
-            }
-            h *= 0.69314718055994530942f;
-            if (has_0) {
-                // the DC term through log1p in float64: p0 may be within 1e-7 of 1 (gravity axis)
-                const double tot64 = static_cast<double>(rest) + dc;
-                const double p0 = dc / tot64, qrest = static_cast<double>(rest) / tot64;
-                h += static_cast<float>((p0 + 1e-30) * (qrest < 0.5 ? log1p(-qrest) : log(p0 + 1e-30)));
-            }
-            sc.ph[w * kNP + p] = h;
-        }
-        __syncthreads();                                   // (B4)
-
-        // ---- finalize: thread (window w, column role [+ 14, ...]) merges the 13 partials of its column
-        if (act) {
-            for (int j = role; j < P.n_cols; j += kThreadsF / 16) {
-                const int kind = P.col[j], ref = P.cref[j];
-                const int q0 = w * kNP;
-                double v;
-                if (kind == MHB_S_ENTROPY) {
-                    float h = 0.f;
-#pragma unroll
-                    for (int i = 0; i < kNP; ++i) h += sc.ph[q0 + i];
-                    v = -static_cast<double>(h);
-                } else if (kind == MHB_S_PEAK_FREQUENCY || kind == MHB_S_PEAK_BIN) {
-                    float best = -1.f;
-                    int arg = 0x7fffffff;
-                    if (P.arg_lo[ref] <= 0 && P.arg_hi[ref] > 0) {
-                        best = static_cast<float>(sc.dc[w]);
-                        arg = 0;
-                    }
-                    const float* pb = sc.pbest + ref * kBW * kNP + q0;
-                    const int* pa = sc.parg + ref * kBW * kNP + q0;
-#pragma unroll
-                    for (int i = 0; i < kNP; ++i) {
-                        const float ob = pb[i];
-                        const int oa = pa[i];
-                        if (ob > best || (ob == best && oa < arg)) {
-                            best = ob;
-                            arg = oa;
-                        }
-                    }
-                    if (arg == 0x7fffffff) v = CUDART_NAN;
-                    else v = kind == MHB_S_PEAK_BIN ? static_cast<double>(arg) : static_cast<double>(arg) * P.bin_hz;
-                } else {
-                    float rest = 0.f;
-#pragma unroll
-                    for (int i = 0; i < kNP; ++i) rest += sc.ptot[q0 + i];
-                    const double dc = sc.dc[w];
-                    const double total = static_cast<double>(rest) + dc;
-                    if (kind == MHB_S_TOTAL_POWER) {
-                        v = total;
-                    } else {
-                        float acc = 0.f;
-                        const float* ps = sc.psum + ref * kBW * kNP + q0;
-#pragma unroll
-                        for (int i = 0; i < kNP; ++i) acc += ps[i];
-                        double bsum = static_cast<double>(acc);
-                        if (P.sum_lo[ref] <= 0 && P.sum_hi[ref] > 0) bsum += dc;
-                        v = kind == MHB_S_BAND_POWER ? bsum : bsum / total;
-                    }
-                }
-                const int64_t o = series * P.o_series + (w0 + w) * P.o_window + j * P.o_col;
-                if (P.out_f32) reinterpret_cast<float*>(P.out)[o] = static_cast<float>(v);
-                else reinterpret_cast<double*>(P.out)[o] = v;
-            }
-        }
-        // no barrier here: the next batch touches msum / buf / the other tile slot only, and its TMA refill of
-        // THIS slot is issued after its barrier (B1), which every thread reaches after finishing this step
+        __syncthreads();                                   // (B2) PSD rows complete; buf free for the next pass A
+        prev_series = series;
+        prev_w0 = w0;
+        prev_nwin = nwin;
         slot ^= 1;
     }
+    // the last batch of this CTA
+    if (!first && role >= kNA)
+        reduce_rows(P, tiles + (slot ^ 1) * kTileElems, R, tid - kNA * 16, prev_series, prev_w0, prev_nwin);
 }
 
 size_t fast_smem_bytes() {
-    return 128 + 2 * sizeof(float) * kTileElems + sizeof(C) * (kBW * kWSB + 25 * kNA + 10 * kNP) +
-           sizeof(float) * (kMeanParts + 1) * kBW + sizeof(uint32_t) * (kMaxSum + kMaxArg) * 2 * 16 + 64;
+    return 128 + 2 * sizeof(float) * kTileElems + sizeof(C) * (kBW * kWSB + 25 * kNA + 10 * kNP) + sizeof(float) * (kBW + 3 * kBW * kNP) + 64;
 }
 
 }  // namespace
@@ -516,30 +500,9 @@ int32_t spectral_fast_try(const float* x, const mhb_windows* geom, int64_t nw, d
     FastPlan P;
     memset(&P, 0, sizeof(P));
     for (int j = 0; j < n_cols; ++j) {
-        const int kind = cols[j];
-        P.col[j] = kind;
-        P.cref[j] = 0;
-        if (kind == MHB_S_BAND_POWER || kind == MHB_S_REL_BAND_POWER) {
-            int r = 0;
-            while (r < P.n_sum && !(P.sum_lo[r] == lo[j] && P.sum_hi[r] == hi[j])) ++r;
-            if (r == P.n_sum) {
-                if (P.n_sum == kMaxSum) return -100;
-                P.sum_lo[r] = lo[j];
-                P.sum_hi[r] = hi[j];
-                ++P.n_sum;
-            }
-            P.cref[j] = r;
-        } else if (kind == MHB_S_PEAK_FREQUENCY || kind == MHB_S_PEAK_BIN) {
-            int r = 0;
-            while (r < P.n_arg && !(P.arg_lo[r] == lo[j] && P.arg_hi[r] == hi[j])) ++r;
-            if (r == P.n_arg) {
-                if (P.n_arg == kMaxArg) return -100;
-                P.arg_lo[r] = lo[j];
-                P.arg_hi[r] = hi[j];
-                ++P.n_arg;
-            }
-            P.cref[j] = r;
-        }
+        P.col[j] = cols[j];
+        P.lo[j] = lo[j];
+        P.hi[j] = hi[j];
     }
     P.x = x;
     P.series_stride = geom->series_stride;
