@@ -5,7 +5,7 @@
 // hrv.power_band / relative_power_band (heart/hrv.py:173-198), density.peak_frequency
 // (generic/frequency/density.py:18-32), information.entropy (generic/information.py:10-20).
 //
-// A CTA (7 warps) owns a batch of BW = 16 consecutive windows of one series; their samples arrive ONCE by a
+// A CTA (8 warps) owns a batch of BW = 16 consecutive windows of one series; their samples arrive ONCE by a
 // 1-D bulk TMA copy (cp.async.bulk + mbarrier, double buffered).  The real W-point DFT is an N = W/2 = 250
 // point complex FFT, factored N = 25 x 10 so that the whole transform is TWO register-resident passes with
 // ONE exchange through shared memory:
@@ -39,7 +39,7 @@ using C = Cx<float>;
 
 constexpr int kW = 500, kS = 250, kN = 250;
 constexpr int kBW = 16;                  // windows per batch
-constexpr int kThreadsF = 224;           // 14 half-warps
+constexpr int kThreadsF = 256;           // 16 half-warps: 10 pass-A roles / 13 pass-B roles / 3 reducer warps
 constexpr int kNA = 10;                  // pass-A threads per window (n2)
 constexpr int kNP = 13;                  // pass-B threads per window (p = 0..12)
 constexpr int kWSB = 251;                // complex stride between windows in buf (odd: conflict free)
@@ -59,6 +59,8 @@ struct FastPlan {
     int32_t n_cols;
     int32_t col[kMaxColsF];              // MHB_S_* kind
     int32_t lo[kMaxColsF], hi[kMaxColsF];   // bin range [lo, hi) of the column
+    int32_t rn[3];                       // columns handled by each of the three reducer warps ...
+    int32_t rcol[3][kMaxColsF];          // ... and which (cost-balanced on the host)
     int32_t use_tma;
 };
 
@@ -126,93 +128,124 @@ __device__ __forceinline__ void dft_composite(C* a) {
 __device__ __forceinline__ void dft10(C* a) { dft_composite<10, 2, 5>(a); }
 __device__ __forceinline__ void dft25(C* a) { dft_composite<25, 5, 5>(a); }
 
-// sum over the 4 lanes of a quad, fixed order (result in every lane)
-__device__ __forceinline__ float quad_sum(float v) {
-    v += __shfl_xor_sync(0xffffffffu, v, 1);
-    v += __shfl_xor_sync(0xffffffffu, v, 2);
-    return v;
-}
+#ifdef MHB_PHASE_TIMING
+__device__ unsigned long long g_phase_cycles[8][8];   // [phase][warp]
+__device__ unsigned long long g_reduce_cycles[16];    // reducer sub-phases (summed over the reducer warps)
+#define MHB_RTICK(i)                                                                                         \
+    do {                                                                                                     \
+        const long long now_ = clock64();                                                                    \
+        if ((threadIdx.x & 31) == 0) atomicAdd(&g_reduce_cycles[i], static_cast<unsigned long long>(now_ - rl)); \
+        rl = clock64();                                                                                      \
+    } while (0)
+#else
+#define MHB_RTICK(i) do {} while (0)
+#endif
 
-// Deferred PSD reducers of one finished batch: 4 lanes (a quad) per window.  Totals and the entropy come from the 13
-// per-thread records pass B left behind (sum, sum y log2 y, exponent); band sums and arg-max read only the bins of
-// their range from the window's PSD row in shared memory.  Runs on the two warps that have no pass-A work while the
-// other five transform the next batch.
+// Deferred PSD reducers of one finished batch.  Three warps (the ones with no pass-A work) share the COLUMNS: warp
+// rw takes columns c = rw, rw + 3, ...; inside a warp a pair of lanes owns a window.  Totals and the entropy come
+// from the 13 per-thread records pass B left behind (sum, sum y log2 y, exponent); band sums and arg-max read only
+// the bins of their range from the window's PSD row in shared memory.  Short instruction streams on purpose: on a
+// saturated SM a warp issues about once every five cycles, so the longest per-warp stream of a phase sets its length.
 struct Records {
     const float* ptot;   // [BW][NP]  sum of the thread's bins (bin 0 excluded)
     const float* ph;     // [BW][NP]  sum y log2 y over the thread's bins, y = psd 2^-pe
     const int* pe;       // [BW][NP]  binary exponent of the thread's ptot
 };
 
+__device__ __forceinline__ float pair_sum(float v) { return v + __shfl_xor_sync(0xffffffffu, v, 1); }
+__device__ __forceinline__ double pair_sum(double v) { return v + __shfl_xor_sync(0xffffffffu, v, 1); }
+
 __device__ __forceinline__ void reduce_rows(const FastPlan& P, const float* __restrict__ slot_base, const Records R,
-                                            int t /*0..63*/, uint32_t series, int64_t w0, int nwin) {
-    const int w = t >> 2, j = t & 3;
+                                            const int4* __restrict__ desc, int n_mine, int lane, uint32_t series,
+                                            int64_t w0, int nwin) {
+#ifdef MHB_PHASE_TIMING
+    long long rl = clock64();
+#endif
+    const int w = lane >> 1, j = lane & 1;
     const bool act = w < nwin;
-    const int wc = act ? w : 0;                       // idle quads alias window 0: they never store
+    const int wc = act ? w : 0;                       // idle pairs alias window 0: they never store
     const double* dcs = reinterpret_cast<const double*>(slot_base);
     const float* prow = slot_base + 2 * kBW + wc * kRowStride;      // prow[k] = |X[k]|^2, k = 1..250
     const double dc = dcs[wc];
     const int q0 = wc * kNP;
-    // lane j of the quad folds records j, j + 4, j + 8 (, 12); quad sums in a fixed order: every lane gets the same bits
-    float r0 = R.ptot[q0 + j], r1 = R.ptot[q0 + j + 4], r2 = R.ptot[q0 + j + 8], r3 = j == 0 ? R.ptot[q0 + 12] : 0.f;
-    double rest = (static_cast<double>(r0) + static_cast<double>(r1)) + (static_cast<double>(r2) + static_cast<double>(r3));
-    rest += __shfl_xor_sync(0xffffffffu, rest, 1);
-    rest += __shfl_xor_sync(0xffffffffu, rest, 2);       // all bins but 0
-    const double total = rest + dc;
-    // Entropy (information.py:10-20): H = -p0 ln p0 - sum_{k>=1} p_k ln p_k.  With E = binary exponent of the total
-    // and f = total 2^-E in [1, 2):
-    //   -(sum_{k>=1} p_k log2 p_k) f = (rest 2^-E) log2 f + sum_t [ tot_t 2^-E (E - e_t) - S_t 2^(e_t - E) ]
-    // every term is O(1), so a float log2 of f (absolute error 2^-22) and a float64 sum of float records suffice.
-    const float tf = static_cast<float>(total);
-    const int E = ((__float_as_int(tf) >> 23) & 0xff) - 127;
-    const float down = __int_as_float((127 - E) << 23);              // 2^-E
-    double acc = 0.0;
+    // lane j folds records j, j + 2, ..., in a fixed order; the pair sum gives both lanes the same bits
+    double rest = 0.0;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int idx = j + 4 * i;
-        if (idx < kNP) {
-            const int e = R.pe[q0 + idx];
-            const int de = E - e;
-            const float u = R.ptot[q0 + idx] * down;
-            const float rel = de < 60 ? __int_as_float((127 - de) << 23) : 0.f;      // 2^(e - E)
-            acc += static_cast<double>(u) * static_cast<double>(de) - static_cast<double>(R.ph[q0 + idx] * rel);
-        }
+    for (int i = 0; i < 7; ++i) {
+        const int idx = j + 2 * i;
+        if (idx < kNP) rest += static_cast<double>(R.ptot[q0 + idx]);
     }
-    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
-    const float f = tf * down;
-    const float hrest2 = static_cast<float>(rest * static_cast<double>(down) * static_cast<double>(__log2f(f)) + acc) *
-                         __fdividef(1.0f, f);
-    const float inv_t = __fdividef(1.0f, tf);
-    const float p0 = static_cast<float>(dc) * inv_t, qrest = static_cast<float>(rest) * inv_t;
-    const float h0 = p0 > 0.f ? -p0 * (qrest < 0.5f ? log1pf(-qrest) : __logf(p0)) : 0.f;   // DC term, log1p near p0 = 1
-    const float h = fmaf(0.69314718055994530942f, hrest2, h0);
+    rest = pair_sum(rest);                            // all bins but 0
+    const double total = rest + dc;
+    MHB_RTICK(0);
 #pragma unroll 1
-    for (int c = 0; c < P.n_cols; ++c) {
-        const int kind = P.col[c];
-        const int lo = P.lo[c], hi = P.hi[c];
+    for (int ci = 0; ci < n_mine; ++ci) {
+        const int4 dsc = desc[ci];                    // (column, kind, lo, hi) from shared memory
+        const int c = dsc.x, kind = dsc.y, lo = dsc.z, hi = dsc.w;
         double v;
         if (kind == MHB_S_TOTAL_POWER) {
             v = total;
         } else if (kind == MHB_S_ENTROPY) {
-            v = total > 0.0 ? static_cast<double>(h) : CUDART_NAN;
+            // information.py:10-20: H = -p0 ln p0 - sum_{k>=1} p_k ln p_k.  With E = binary exponent of the total and
+            // f = total 2^-E in [1, 2):
+            //   -(sum_{k>=1} p_k log2 p_k) f = (rest 2^-E) log2 f + sum_t [ tot_t 2^-E (E - e_t) - S_t 2^(e_t - E) ]
+            // every term is O(1): a float log2 of f (absolute error 2^-22) and a float64 sum of float records suffice
+            const float tf = static_cast<float>(total);
+            const int E = ((__float_as_int(tf) >> 23) & 0xff) - 127;
+            const float down = __int_as_float((127 - E) << 23);              // 2^-E
+            double acc = 0.0;
+#pragma unroll
+            for (int i = 0; i < 7; ++i) {
+                const int idx = j + 2 * i;
+                if (idx < kNP) {
+                    const int e = R.pe[q0 + idx];
+                    const int de = E - e;
+                    const float u = R.ptot[q0 + idx] * down;
+                    const float rel = de < 60 ? __int_as_float((127 - de) << 23) : 0.f;      // 2^(e - E)
+                    acc += static_cast<double>(u) * static_cast<double>(de) - static_cast<double>(R.ph[q0 + idx] * rel);
+                }
+            }
+            acc = pair_sum(acc);
+            const float f = tf * down;
+            const float hrest2 = static_cast<float>(rest * static_cast<double>(down) * static_cast<double>(__log2f(f)) + acc) *
+                                 __fdividef(1.0f, f);
+            const float inv_t = __fdividef(1.0f, tf);
+            const float p0 = static_cast<float>(dc) * inv_t, qrest = static_cast<float>(rest) * inv_t;
+            const float h0 = p0 > 0.f ? -p0 * (qrest < 0.5f ? log1pf(-qrest) : __logf(p0)) : 0.f;   // log1p near p0 = 1
+            v = total > 0.0 ? static_cast<double>(fmaf(0.69314718055994530942f, hrest2, h0)) : CUDART_NAN;
         } else if (kind == MHB_S_BAND_POWER || kind == MHB_S_REL_BAND_POWER) {
-            float acc = 0.f;
-#pragma unroll 4
-            for (int k = (lo > 1 ? lo : 1) + j; k < hi; k += 4) acc += prow[k];
-            double bsum = static_cast<double>(quad_sum(acc));
+            float a0 = 0.f, a1 = 0.f;
+            int k = (lo > 1 ? lo : 1) + j;
+            for (; k + 2 < hi; k += 4) {
+                a0 += prow[k];
+                a1 += prow[k + 2];
+            }
+            if (k < hi) a0 += prow[k];
+            double bsum = static_cast<double>(pair_sum(a0 + a1));
             if (lo <= 0 && hi > 0) bsum += dc;
             v = kind == MHB_S_BAND_POWER ? bsum : bsum / total;
         } else {                                      // peak frequency / bin: first maximum in [lo, hi)
-            float best = -1.f;
-            int arg = 0x7fffffff;
-#pragma unroll 4
-            for (int k = (lo > 1 ? lo : 1) + j; k < hi; k += 4) {
-                const float pv = prow[k];
-                if (pv > best) {
-                    best = pv;
-                    arg = k;
-                }
+            // four independent running maxima over interleaved bins (the compare-select chain is the latency), merged
+            // with "lower bin wins a tie" so the result is the first maximum
+            float b0 = -1.f, b1 = -1.f, b2 = -1.f, b3 = -1.f;
+            int g0 = 0x7fffffff, g1 = 0x7fffffff, g2 = 0x7fffffff, g3 = 0x7fffffff;
+            int k = (lo > 1 ? lo : 1) + j;
+            for (; k + 6 < hi; k += 8) {
+                const float v0 = prow[k], v1 = prow[k + 2], v2 = prow[k + 4], v3 = prow[k + 6];
+                if (v0 > b0) { b0 = v0; g0 = k; }
+                if (v1 > b1) { b1 = v1; g1 = k + 2; }
+                if (v2 > b2) { b2 = v2; g2 = k + 4; }
+                if (v3 > b3) { b3 = v3; g3 = k + 6; }
             }
+            for (; k < hi; k += 2) {
+                const float v0 = prow[k];
+                if (v0 > b0) { b0 = v0; g0 = k; }
+            }
+            if (b1 > b0 || (b1 == b0 && g1 < g0)) { b0 = b1; g0 = g1; }
+            if (b3 > b2 || (b3 == b2 && g3 < g2)) { b2 = b3; g2 = g3; }
+            if (b2 > b0 || (b2 == b0 && g2 < g0)) { b0 = b2; g0 = g2; }
+            float best = b0;
+            int arg = g0;
             if (j == 0 && lo <= 0 && hi > 0) {        // bin 0 competes too; ties go to the lower bin
                 const float d = static_cast<float>(dc);
                 if (d >= best) {
@@ -220,19 +253,17 @@ __device__ __forceinline__ void reduce_rows(const FastPlan& P, const float* __re
                     arg = 0;
                 }
             }
-#pragma unroll
-            for (int o = 1; o <= 2; o <<= 1) {
-                const float ob = __shfl_xor_sync(0xffffffffu, best, o);
-                const int oa = __shfl_xor_sync(0xffffffffu, arg, o);
-                if (ob > best || (ob == best && oa < arg)) {
-                    best = ob;
-                    arg = oa;
-                }
+            const float ob = __shfl_xor_sync(0xffffffffu, best, 1);
+            const int oa = __shfl_xor_sync(0xffffffffu, arg, 1);
+            if (ob > best || (ob == best && oa < arg)) {
+                best = ob;
+                arg = oa;
             }
             if (arg == 0x7fffffff) v = CUDART_NAN;
             else v = kind == MHB_S_PEAK_BIN ? static_cast<double>(arg) : static_cast<double>(arg) * P.bin_hz;
         }
-        if (act && j == (c & 3)) {                    // the four lanes of the quad share the stores
+        MHB_RTICK(1 + c);
+        if (act && j == 0) {
             const int64_t o = static_cast<int64_t>(series) * P.o_series + (w0 + w) * P.o_window + c * P.o_col;
             if (P.out_f32) reinterpret_cast<float*>(P.out)[o] = static_cast<float>(v);
             else reinterpret_cast<double*>(P.out)[o] = v;
@@ -240,7 +271,22 @@ __device__ __forceinline__ void reduce_rows(const FastPlan& P, const float* __re
     }
 }
 
+#ifdef MHB_PHASE_TIMING
+#define MHB_TICK(ph)                                                             \
+    do {                                                                         \
+        const long long now_ = clock64();                                        \
+        if ((threadIdx.x & 31) == 0) tacc[ph] += now_ - tlast;                   \
+        tlast = clock64();                                                       \
+    } while (0)
+#else
+#define MHB_TICK(ph) do {} while (0)
+#endif
+
 __global__ void __launch_bounds__(kThreadsF, 3) spectral_fast_kernel(const FastPlan P) {
+#ifdef MHB_PHASE_TIMING
+    long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long tlast = clock64();
+#endif
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);                 // 2 barriers
     float* tiles = reinterpret_cast<float*>(smem_raw + 128);                // 2 x kTileElems
@@ -252,6 +298,14 @@ __global__ void __launch_bounds__(kThreadsF, 3) spectral_fast_kernel(const FastP
     float* rec_h = rec_tot + kBW * kNP;
     int* rec_e = reinterpret_cast<int*>(rec_h + kBW * kNP);
     const Records R = {rec_tot, rec_h, rec_e};
+    int4* desc = reinterpret_cast<int4*>((reinterpret_cast<uintptr_t>(rec_e + kBW * kNP) + 15) & ~uintptr_t(15));   // [3][kMaxColsF]
+    for (int i = threadIdx.x; i < 3 * kMaxColsF; i += kThreadsF) {
+        const int rwi = i / kMaxColsF, ci = i - rwi * kMaxColsF;
+        if (ci < P.rn[rwi]) {
+            const int c = P.rcol[rwi][ci];
+            desc[i] = make_int4(c, P.col[c], P.lo[c], P.hi[c]);
+        }
+    }
     const int tid = threadIdx.x;
     const int w = tid & 15;              // window of the batch this thread transforms
     const int role = tid >> 4;           // half-warp index 0..13
@@ -345,6 +399,7 @@ __global__ void __launch_bounds__(kThreadsF, 3) spectral_fast_kernel(const FastP
             __syncthreads();
         }
         const bool act = w < nwin;
+        MHB_TICK(0);                                       // tile wait
 
         if (role < kNA) {
             // ---- pass A (warps 0-4): 25-point DFTs of the stride-10 subsequences, inter-pass twiddle, exchange
@@ -380,10 +435,13 @@ __global__ void __launch_bounds__(kThreadsF, 3) spectral_fast_kernel(const FastP
                 }
             }
         } else if (!first) {
-            // ---- warps 5-6: PSD reducers of the PREVIOUS batch, whose rows sit in the other (consumed) tile slot
-            reduce_rows(P, tiles + (slot ^ 1) * kTileElems, R, tid - kNA * 16, prev_series, prev_w0, prev_nwin);
+            // ---- warps 5-7: PSD reducers of the PREVIOUS batch, whose rows sit in the other (consumed) tile slot
+            reduce_rows(P, tiles + (slot ^ 1) * kTileElems, R, desc + ((tid >> 5) - 5) * kMaxColsF, P.rn[(tid >> 5) - 5], tid & 31,
+                        prev_series, prev_w0, prev_nwin);
         }
+        MHB_TICK(1);                                       // pass A / deferred reducers
         __syncthreads();                                   // (B1) pass A done, previous batch fully reduced
+        MHB_TICK(2);                                       // wait at B1
         // refill the slot the previous batch used (its PSD rows are dead now)
         if (tid == 0 && !first) {
             uint32_t s2 = series, b2 = bi;
@@ -474,19 +532,26 @@ __global__ void __launch_bounds__(kThreadsF, 3) spectral_fast_kernel(const FastP
             rec_h[q] = ha + hb;
             rec_e[q] = eb - 127;
         }
+        MHB_TICK(3);                                       // pass B
         __syncthreads();                                   // (B2) PSD rows complete; buf free for the next pass A
+        MHB_TICK(4);                                       // wait at B2
         prev_series = series;
         prev_w0 = w0;
         prev_nwin = nwin;
         slot ^= 1;
     }
+#ifdef MHB_PHASE_TIMING
+    if ((threadIdx.x & 31) == 0)
+        for (int ph = 0; ph < 8; ++ph) atomicAdd(&g_phase_cycles[ph][threadIdx.x >> 5], static_cast<unsigned long long>(tacc[ph]));
+#endif
     // the last batch of this CTA
     if (!first && role >= kNA)
-        reduce_rows(P, tiles + (slot ^ 1) * kTileElems, R, tid - kNA * 16, prev_series, prev_w0, prev_nwin);
+        reduce_rows(P, tiles + (slot ^ 1) * kTileElems, R, desc + ((tid >> 5) - 5) * kMaxColsF, P.rn[(tid >> 5) - 5], tid & 31,
+                        prev_series, prev_w0, prev_nwin);
 }
 
 size_t fast_smem_bytes() {
-    return 128 + 2 * sizeof(float) * kTileElems + sizeof(C) * (kBW * kWSB + 25 * kNA + 10 * kNP) + sizeof(float) * (kBW + 3 * kBW * kNP) + 64;
+    return 128 + 2 * sizeof(float) * kTileElems + sizeof(C) * (kBW * kWSB + 25 * kNA + 10 * kNP) + sizeof(float) * (kBW + 3 * kBW * kNP) + 16 * 3 * kMaxColsF + 64 + 16;
 }
 
 }  // namespace
@@ -503,6 +568,29 @@ int32_t spectral_fast_try(const float* x, const mhb_windows* geom, int64_t nw, d
         P.col[j] = cols[j];
         P.lo[j] = lo[j];
         P.hi[j] = hi[j];
+    }
+    {   // longest-processing-time-first assignment of the columns to the three reducer warps
+        int cost[kMaxColsF], order[kMaxColsF], load[3] = {0, 0, 0};
+        for (int j = 0; j < n_cols; ++j) {
+            const int span = hi[j] > lo[j] ? hi[j] - lo[j] : 0;
+            const int kind = cols[j];
+            cost[j] = kind == MHB_S_TOTAL_POWER ? 40 : kind == MHB_S_ENTROPY ? 160
+                      : (kind == MHB_S_BAND_POWER ? 80 + span : kind == MHB_S_REL_BAND_POWER ? 120 + span : 100 + 3 * span);
+            order[j] = j;
+        }
+        for (int a = 1; a < n_cols; ++a)
+            for (int b2 = a; b2 > 0 && cost[order[b2]] > cost[order[b2 - 1]]; --b2) {
+                const int tmp = order[b2];
+                order[b2] = order[b2 - 1];
+                order[b2 - 1] = tmp;
+            }
+        for (int a = 0; a < n_cols; ++a) {
+            int best = 0;
+            for (int r = 1; r < 3; ++r)
+                if (load[r] < load[best]) best = r;
+            P.rcol[best][P.rn[best]++] = order[a];
+            load[best] += cost[order[a]];
+        }
     }
     P.x = x;
     P.series_stride = geom->series_stride;
