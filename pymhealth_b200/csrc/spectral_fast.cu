@@ -125,6 +125,30 @@ __device__ __forceinline__ void dft_composite(C* a) {
         for (int t1 = 0; t1 < RA; ++t1) a[t2 + RB * t1] = g[t1];
     }
 }
+// Same transform, but every output is handed to `emit(t, value)` as soon as its last butterfly is done, so the caller's
+// twiddle loads / stores interleave with the remaining butterflies instead of queueing behind them.
+template <int R, int RA, int RB, typename Emit>
+__device__ __forceinline__ void dft_composite_emit(C* a, Emit emit) {
+    C f[RA][RB];
+#pragma unroll
+    for (int u1 = 0; u1 < RA; ++u1) {
+#pragma unroll
+        for (int u2 = 0; u2 < RB; ++u2) f[u1][u2] = a[RA * u2 + u1];
+        dft_prime<RB>(f[u1]);
+#pragma unroll
+        for (int t2 = 1; t2 < RB; ++t2)
+            if (u1 > 0) f[u1][t2] = cmul(f[u1][t2], ctw<R>(u1 * t2));
+    }
+#pragma unroll
+    for (int t2 = 0; t2 < RB; ++t2) {
+        C g[RA];
+#pragma unroll
+        for (int u1 = 0; u1 < RA; ++u1) g[u1] = f[u1][t2];
+        dft_prime<RA>(g);
+#pragma unroll
+        for (int t1 = 0; t1 < RA; ++t1) emit(t2 + RB * t1, g[t1]);
+    }
+}
 __device__ __forceinline__ void dft10(C* a) { dft_composite<10, 2, 5>(a); }
 __device__ __forceinline__ void dft25(C* a) { dft_composite<25, 5, 5>(a); }
 
@@ -310,18 +334,8 @@ __global__ void __launch_bounds__(kThreadsF, 3) spectral_fast_kernel(const FastP
     const int w = tid & 15;              // window of the batch this thread transforms
     const int role = tid >> 4;           // half-warp index 0..13
 
-    for (int i = tid; i < 25 * kNA; i += kThreadsF) {
-        const int k1 = i / kNA, n2 = i - k1 * kNA;
-        double sn, cs;
-        sincospi(-2.0 * static_cast<double>(k1 * n2) / 250.0, &sn, &cs);
-        twA[i] = {static_cast<float>(cs), static_cast<float>(sn)};
-    }
-    for (int i = tid; i < 10 * kNP; i += kThreadsF) {
-        const int k2 = i / kNP, p = i - k2 * kNP;
-        double sn, cs;
-        sincospi(-2.0 * static_cast<double>(p + 25 * k2) / 500.0, &sn, &cs);
-        twB[i] = {static_cast<float>(cs), static_cast<float>(sn)};
-    }
+    for (int i = tid; i < 25 * kNA; i += kThreadsF) twA[i] = {kTw250[i].x, kTw250[i].y};
+    for (int i = tid; i < 10 * kNP; i += kThreadsF) twB[i] = {kTw500[i].x, kTw500[i].y};
     if (tid == 0) {
         mbar_init(&full[0], 1);
         mbar_init(&full[1], 1);
@@ -378,32 +392,38 @@ __global__ void __launch_bounds__(kThreadsF, 3) spectral_fast_kernel(const FastP
     int64_t prev_w0 = 0;
     int prev_nwin = 0;
 
-    for (; series < n_series; advance(series, bi)) {
-        int64_t w0, goff;
-        int nwin, n_valid;
-        geom_of(series, bi, w0, nwin, goff, n_valid);
+    // one iteration per batch plus a last one that only reduces the final batch's rows (`live` false)
+    for (;; advance(series, bi)) {
+        const bool live = series < n_series;
+        if (!live && first) break;                         // this CTA had no batch at all
+        int64_t w0 = 0, goff = 0;
+        int nwin = 0, n_valid = 0;
         float* tile = tiles + slot * kTileElems;
-        const int n_load = (n_valid + 3) & ~3;
-        if (tma_ok(goff, n_load)) {
-            if (slot == 0) {
-                mbar_wait(&full[0], parity0);
-                parity0 ^= 1;
+        if (live) {
+            geom_of(series, bi, w0, nwin, goff, n_valid);
+            const int n_load = (n_valid + 3) & ~3;
+            if (tma_ok(goff, n_load)) {
+                if (slot == 0) {
+                    mbar_wait(&full[0], parity0);
+                    parity0 ^= 1;
+                } else {
+                    mbar_wait(&full[1], parity1);
+                    parity1 ^= 1;
+                }
             } else {
-                mbar_wait(&full[1], parity1);
-                parity1 ^= 1;
+                // unaligned base or the last few samples of the buffer: guarded cooperative copy.  The slot held the
+                // PSD rows of the batch before the previous one; they were reduced before the barriers of the last
+                // iteration.
+                for (int i = tid; i < n_valid; i += kThreadsF) tile[i] = P.x[goff + i];
+                __syncthreads();
             }
-        } else {
-            // unaligned base or the last few samples of the buffer: guarded cooperative copy.  The slot held the PSD
-            // rows of the batch before the previous one; they were reduced before the barriers of the last iteration.
-            for (int i = tid; i < n_valid; i += kThreadsF) tile[i] = P.x[goff + i];
-            __syncthreads();
         }
         const bool act = w < nwin;
         MHB_TICK(0);                                       // tile wait
 
         if (role < kNA) {
             // ---- pass A (warps 0-4): 25-point DFTs of the stride-10 subsequences, inter-pass twiddle, exchange
-            if (act) {
+            if (act && live) {
                 const int n2 = role;
                 // pivot of the transform: a 16-sample estimate of the window mean (any value near the mean works:
                 // bin 0 is restored exactly in pass B; the pivot only keeps a large DC out of the float32 dynamic
@@ -439,6 +459,7 @@ __global__ void __launch_bounds__(kThreadsF, 3) spectral_fast_kernel(const FastP
             reduce_rows(P, tiles + (slot ^ 1) * kTileElems, R, desc + ((tid >> 5) - 5) * kMaxColsF, P.rn[(tid >> 5) - 5], tid & 31,
                         prev_series, prev_w0, prev_nwin);
         }
+        if (!live) break;
         MHB_TICK(1);                                       // pass A / deferred reducers
         __syncthreads();                                   // (B1) pass A done, previous batch fully reduced
         MHB_TICK(2);                                       // wait at B1
@@ -450,63 +471,55 @@ __global__ void __launch_bounds__(kThreadsF, 3) spectral_fast_kernel(const FastP
         }
         first = false;
 
-        // ---- pass B: 10-point DFTs -> untangle -> |X|^2 -> PSD row in the consumed tile slot
-        const bool has_b = role < kNP - 1;                 // p = role + 1 = 1..12
-        const bool has_0 = role == kNP - 1;                // p = 0 lives alone in the lower half of warp 6
-        if ((has_b || has_0) && act) {
-            const int p = has_b ? role + 1 : 0;
+        // ---- pass B: 10-point DFTs -> untangle -> |X|^2 -> PSD row in the consumed tile slot.
+        // Thread (w, p) transforms columns p and 25 - p of buf: A[k2] = Z[p + 25 k2] / 2, B[k2] = Z[25 - p + 25 k2] / 2,
+        // the partner of bin k = p + 25 k2 being N - k = (25 - p) + 25 (9 - k2).  p = 0 runs the SAME code: it loads
+        // column 0 twice and rotates, B[m] = A[(m + 1) mod 10], because the partner of 25 k2 is 25 (10 - k2); its
+        // k2 = 0 pair then yields bins 0 and N, and its high-set values k2 >= 1 are duplicates of its low set.
+        if (role < kNP && act) {
+            const int p = role < kNP - 1 ? role + 1 : 0;   // p = 0 lives alone in the lower half of warp 6
+            const bool p0 = p == 0;
             const C* bw = buf + w * kWSB;
             float* prow = tile + 2 * kBW + w * kRowStride;
-            C A[10];
+            C A[10], B[10];
+            const int pb = p0 ? 0 : 25 - p;
 #pragma unroll
-            for (int n2 = 0; n2 < 10; ++n2) A[n2] = bw[n2 * 25 + p];
-            dft10(A);                                      // A[k2] = Z[p + 25 k2] / 2
-            float psd[20];                                 // this thread's bins (unused slots stay 0)
-            if (has_b) {
-                C B[10];
+            for (int n2 = 0; n2 < 10; ++n2) {
+                A[n2] = bw[n2 * 25 + p];
+                B[n2] = bw[n2 * 25 + pb];
+            }
+            dft10(A);
+            dft10(B);
+            if (p0) {
+                const C b0 = B[0];
 #pragma unroll
-                for (int n2 = 0; n2 < 10; ++n2) B[n2] = bw[n2 * 25 + 25 - p];
-                dft10(B);                                  // B[k2] = Z[25 - p + 25 k2] / 2
-                float* lo_ptr = prow + p;                  // bin p + 25 k2
-                float* hi_ptr = prow + kN - p;             // bin 250 - p - 25 k2
+                for (int m = 0; m < 9; ++m) B[m] = B[m + 1];
+                B[9] = b0;
+            }
+            float psd[20];                                 // this thread's bins: [2 k2] low set, [2 k2 + 1] high set
+            float* lo_ptr = prow + p;                      // bin p + 25 k2
+            float* hi_ptr = prow + kN - p;                 // bin 250 - p - 25 k2
 #pragma unroll
-                for (int k2 = 0; k2 < 10; ++k2) {
-                    const C zk = A[k2], zn = B[9 - k2];   // (k, N - k), k = p + 25 k2
-                    const C t2 = twB[k2 * kNP + p];
-                    const C e = {zk.x + zn.x, zk.y - zn.y};
-                    const C o = {zk.y + zn.y, zn.x - zk.x};
-                    const C t = cmul(o, t2);
-                    const float ar = e.x + t.x, ai = e.y + t.y, br = e.x - t.x, bi2 = e.y - t.y;
-                    psd[2 * k2] = fmaf(ar, ar, ai * ai);
-                    psd[2 * k2 + 1] = fmaf(br, br, bi2 * bi2);
-                    lo_ptr[25 * k2] = psd[2 * k2];
-                    hi_ptr[-25 * k2] = psd[2 * k2 + 1];
-                }
-            } else {
-                // p = 0: Z[25 k2]; pairs (k2, 10 - k2) for k2 = 1..4, the self pair k2 = 5, and bins 0 / N from Z[0]
-#pragma unroll
-                for (int i = 0; i < 20; ++i) psd[i] = 0.f;
-#pragma unroll
-                for (int k2 = 1; k2 <= 5; ++k2) {
-                    const C zk = A[k2], zn = A[10 - k2];
-                    const C t2 = twB[k2 * kNP];
-                    const C e = {zk.x + zn.x, zk.y - zn.y};
-                    const C o = {zk.y + zn.y, zn.x - zk.x};
-                    const C t = cmul(o, t2);
-                    const float ar = e.x + t.x, ai = e.y + t.y, br = e.x - t.x, bi2 = e.y - t.y;
-                    psd[2 * k2] = fmaf(ar, ar, ai * ai);
-                    prow[25 * k2] = psd[2 * k2];                                // bin 25 k2
-                    if (k2 < 5) {
-                        psd[2 * k2 + 1] = fmaf(br, br, bi2 * bi2);
-                        prow[kN - 25 * k2] = psd[2 * k2 + 1];                   // bin 250 - 25 k2
-                    }
-                }
-                const float xn = 2.f * (A[0].x - A[0].y);
-                psd[0] = xn * xn;
-                prow[kN] = psd[0];                                              // bin N = 250 (Nyquist)
+            for (int k2 = 0; k2 < 10; ++k2) {
+                const C zk = A[k2], zn = B[9 - k2];       // (k, N - k), k = p + 25 k2
+                const C t2 = twB[k2 * kNP + p];
+                const C e = {zk.x + zn.x, zk.y - zn.y};
+                const C o = {zk.y + zn.y, zn.x - zk.x};
+                const C t = cmul(o, t2);
+                const float ar = e.x + t.x, ai = e.y + t.y, br = e.x - t.x, bi2 = e.y - t.y;
+                psd[2 * k2] = fmaf(ar, ar, ai * ai);
+                psd[2 * k2 + 1] = fmaf(br, br, bi2 * bi2);
+                hi_ptr[-25 * k2] = psd[2 * k2 + 1];        // p = 0, k2 >= 1: rewritten below by the low-set twin
+                lo_ptr[25 * k2] = psd[2 * k2];             // p = 0, k2 = 0 lands in the unused cell prow[0]
+            }
+            if (p0) {
+                // exact bin 0: FFT(x - m)[0] + W m in float64; the records must count every bin once
                 const double x0 = 2.0 * (static_cast<double>(A[0].x) + static_cast<double>(A[0].y)) +
                                   static_cast<double>(kW) * static_cast<double>(piv[w]);
-                reinterpret_cast<double*>(tile)[w] = x0 * x0;                   // exact DC: FFT(x - m)[0] + W m
+                reinterpret_cast<double*>(tile)[w] = x0 * x0;
+                psd[0] = 0.f;
+#pragma unroll
+                for (int k2 = 1; k2 < 10; ++k2) psd[2 * k2 + 1] = 0.f;
             }
             // records for the deferred reducers: total of the thread's bins, and the entropy partial in ONE pass: with
             // y = psd 2^-e (e = binary exponent of this thread's total -- an exact scaling that keeps |log2 y| small for
@@ -544,10 +557,6 @@ __global__ void __launch_bounds__(kThreadsF, 3) spectral_fast_kernel(const FastP
     if ((threadIdx.x & 31) == 0)
         for (int ph = 0; ph < 8; ++ph) atomicAdd(&g_phase_cycles[ph][threadIdx.x >> 5], static_cast<unsigned long long>(tacc[ph]));
 #endif
-    // the last batch of this CTA
-    if (!first && role >= kNA)
-        reduce_rows(P, tiles + (slot ^ 1) * kTileElems, R, desc + ((tid >> 5) - 5) * kMaxColsF, P.rn[(tid >> 5) - 5], tid & 31,
-                        prev_series, prev_w0, prev_nwin);
 }
 
 size_t fast_smem_bytes() {
