@@ -22,16 +22,72 @@ namespace {
 constexpr double kEarthDiameterKm = 12742.018;            // distance.py:8,18  (2 * 6371.009)
 constexpr double kDeg = 0.017453292519943295;             // pi / 180, np.radians
 
+// sin / asin of the SMALL arguments this path lives on (half-differences of neighbouring fixes are ~1e-7 rad, a trace
+// spans ~1e-3 rad): below the cut the odd Taylor polynomial is exact to < 1e-19 relative (last dropped term
+// x^16 / 17! and ~0.022 y^10), so it is as accurate as the library routine (<= 1 ulp) without its range reduction
+// (53 -> ~12 instructions per call); larger arguments take the library path.
+__device__ __forceinline__ double sin_fast(double x) {
+    if (fabs(x) > 0.5) return sin(x);
+    const double s = x * x;
+    double p = 1.0 / 1307674368000.0;               // 1 / 15!
+    p = fma(p, s, -1.0 / 6227020800.0);             // 1 / 13!
+    p = fma(p, s, 1.0 / 39916800.0);                // 1 / 11!
+    p = fma(p, s, -1.0 / 362880.0);                 // 1 / 9!
+    p = fma(p, s, 1.0 / 5040.0);                    // 1 / 7!
+    p = fma(p, s, -1.0 / 120.0);                    // 1 / 5!
+    p = fma(p, s, 1.0 / 6.0);                       // 1 / 3!
+    return fma(-x * s, p, x);
+}
+// cos of a latitude in radians: |x| <= pi/2 always holds for valid data, so two Taylor kernels replace the library's
+// general argument reduction: cos x on |x| <= pi/4 (last dropped term x^18 / 18! < 3e-18), and sin(pi/2 - |x|) with
+// pi/2 split in two doubles above that.  Anything outside falls back to cos().
+__device__ __forceinline__ double cos_lat(double x) {
+    const double ax = fabs(x);
+    if (!(ax <= 1.5707963267948966)) return cos(x);
+    if (ax <= 0.7853981633974483) {
+        const double s = x * x;
+        double p = 1.0 / 20922789888000.0;           // 1 / 16!
+        p = fma(p, s, -1.0 / 87178291200.0);         // 1 / 14!
+        p = fma(p, s, 1.0 / 479001600.0);            // 1 / 12!
+        p = fma(p, s, -1.0 / 3628800.0);             // 1 / 10!
+        p = fma(p, s, 1.0 / 40320.0);                // 1 / 8!
+        p = fma(p, s, -1.0 / 720.0);                 // 1 / 6!
+        p = fma(p, s, 1.0 / 24.0);                   // 1 / 4!
+        p = fma(p, s, -0.5);
+        return fma(p, s, 1.0);
+    }
+    const double y = (1.5707963267948966 - ax) + 6.123233995736766e-17;      // pi/2 = hi + lo
+    const double s = y * y;
+    double p = 1.0 / 355687428096000.0;              // 1 / 17!
+    p = fma(p, s, -1.0 / 1307674368000.0);           // 1 / 15!
+    p = fma(p, s, 1.0 / 6227020800.0);               // 1 / 13!
+    p = fma(p, s, -1.0 / 39916800.0);                // 1 / 11!
+    p = fma(p, s, 1.0 / 362880.0);                   // 1 / 9!
+    p = fma(p, s, -1.0 / 5040.0);                    // 1 / 7!
+    p = fma(p, s, 1.0 / 120.0);                      // 1 / 5!
+    p = fma(p, s, -1.0 / 6.0);                       // 1 / 3!
+    return fma(y * s, p, y);
+}
+__device__ __forceinline__ double asin_fast(double y) {
+    if (!(fabs(y) < 0.02)) return asin(y);
+    const double s = y * y;
+    double p = 105.0 / 3456.0;
+    p = fma(p, s, 15.0 / 336.0);
+    p = fma(p, s, 3.0 / 40.0);
+    p = fma(p, s, 1.0 / 6.0);
+    return fma(y * s, p, y);
+}
+
 // distance.py:4-19 -- every input converted to radians BEFORE the subtraction
 __device__ __forceinline__ double haversine(double lat1, double lon1, double lat2, double lon2) {
     // products rounded BEFORE the subtraction, as numpy does (no fused multiply-subtract): the step
     // between two 1 Hz fixes is ~1e-7 rad, and a contracted fma(lat2, k, -a1) changes it by ~1e-10 relative
     const double a1 = __dmul_rn(lat1, kDeg), a2 = __dmul_rn(lat2, kDeg);
     const double o1 = __dmul_rn(lon1, kDeg), o2 = __dmul_rn(lon2, kDeg);
-    const double sa = sin(__dsub_rn(a2, a1) / 2.0);
-    const double so = sin(__dsub_rn(o2, o1) / 2.0);
-    const double h = sa * sa + (cos(a1) * cos(a2) * (so * so));
-    return kEarthDiameterKm * asin(sqrt(h));
+    const double sa = sin_fast(__dsub_rn(a2, a1) / 2.0);
+    const double so = sin_fast(__dsub_rn(o2, o1) / 2.0);
+    const double h = sa * sa + (cos_lat(a1) * cos_lat(a2) * (so * so));
+    return kEarthDiameterKm * asin_fast(sqrt(h));
 }
 
 __global__ void haversine_elementwise_kernel(const double* __restrict__ lat1, const double* __restrict__ lon1,
@@ -83,6 +139,41 @@ __device__ __forceinline__ double plogp(double cnt, double n) {
     return p * log(p);
 }
 
+// haversine split in two so that shared sub-expressions are evaluated once per point:
+//   hav_h   = sin^2(dlat / 2) + cos(lat1) cos(lat2) sin^2(dlon / 2)   (inputs already in radians, cosines supplied)
+//   hav_km  = 2 r asin(sqrt(h))
+// Same operations in the same order as haversine() above.
+__device__ __forceinline__ double hav_h(double a1, double o1, double c1, double a2, double o2, double c2) {
+    const double sa = sin_fast(__dsub_rn(a2, a1) / 2.0);
+    const double so = sin_fast(__dsub_rn(o2, o1) / 2.0);
+    return sa * sa + (c1 * c2 * (so * so));
+}
+__device__ __forceinline__ double hav_km(double h) { return kEarthDiameterKm * asin_fast(sqrt(h)); }
+
+// Comparison of a distance with a threshold through h: d(h) = 2 r asin(sqrt(h)) is monotone, so away from the
+// threshold the comparison of h with sin^2(D / 2r) decides; inside a 1e-9 relative guard band the distance itself is
+// evaluated and compared exactly as the reference would (bit-exact counts and labels).
+struct HavThreshold {
+    double d, h, lo, hi;
+    __device__ __forceinline__ void set(double dist) {
+        d = dist;
+        const double sn = sin(dist / kEarthDiameterKm);
+        h = sn * sn;
+        lo = h * (1.0 - 1e-9);
+        hi = h * (1.0 + 1e-9);
+        if (!(dist >= 0.0)) lo = hi = h = -1.0;              // negative / NaN thresholds: always evaluate exactly
+        if (dist >= kEarthDiameterKm * 1.5) lo = hi = h = -1.0;    // beyond asin's range: evaluate exactly
+    }
+    __device__ __forceinline__ bool greater(double hv) const {     // hav_km(hv) > d
+        if (h < 0.0 || (hv >= lo && hv <= hi)) return hav_km(hv) > d;
+        return hv > h;
+    }
+    __device__ __forceinline__ bool less(double hv) const {        // hav_km(hv) < d
+        if (h < 0.0 || (hv >= lo && hv <= hi)) return hav_km(hv) < d;
+        return hv < h;
+    }
+};
+
 // One warp per segment.
 __global__ void __launch_bounds__(256) location_segments_kernel(
     const double* __restrict__ lat, const double* __restrict__ lon, const int64_t* __restrict__ t,
@@ -91,6 +182,9 @@ __global__ void __launch_bounds__(256) location_segments_kernel(
     const int lane = threadIdx.x & 31;
     const int64_t warp0 = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 5;
     const int64_t nwarps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+    HavThreshold th_home, th_stay;
+    th_home.set(limit);
+    th_stay.set(stay_dist);
     for (int64_t seg = warp0; seg < n_segments; seg += nwarps) {
         const int64_t a = offs[seg], b = offs[seg + 1];
         const int64_t n = b - a;
@@ -113,21 +207,38 @@ __global__ void __launch_bounds__(256) location_segments_kernel(
             s2 += lo[i];
         }
         const double mlat = warp_sum(s1) / nd, mlon = warp_sum(s2) / nd;
-        // ---- pass B: variances, gyration, path length, home statistics
+        // ---- pass B: variances, gyration, path length, home statistics.  Per point: ONE cosine (its own latitude,
+        // shared by the three haversines it takes part in; the previous point's comes from the neighbouring lane),
+        // six sines, and asin / sqrt only where the distance itself is needed (gyration, path length).
         const double hlat = home[2 * seg], hlon = home[2 * seg + 1];
-        double vlat = 0, vlon = 0, gyr = 0, path = 0, dmax = 0;
+        const double am = __dmul_rn(mlat, kDeg), om = __dmul_rn(mlon, kDeg), cm = cos_lat(am);
+        const double ah = __dmul_rn(hlat, kDeg), oh = __dmul_rn(hlon, kDeg), ch = cos_lat(ah);
+        double vlat = 0, vlon = 0, gyr = 0, path = 0, hmax = 0;
         unsigned long long near = 0;
-        for (int64_t i = lane; i < n; i += 32) {
-            const double x = la[i], y = lo[i];
-            const double dx = x - mlat, dy = y - mlon;
-            vlat += dx * dx;
-            vlon += dy * dy;
-            const double dc = haversine(x, y, mlat, mlon);
-            gyr += dc * dc;
-            if (i > 0) path += haversine(la[i - 1], lo[i - 1], x, y);
-            const double dh = haversine(hlat, hlon, x, y);          // haversine_vector(home, points), features.py:52-53
-            dmax = fmax(dmax, dh);
-            near += (dh < limit) ? 1ull : 0ull;                      // strict <, features.py:83-84
+        double carry_c = 0.0;                       // cos(latitude) of the last point of the previous 32-point step
+        for (int64_t base = 0; base < n; base += 32) {
+            const int64_t i = base + lane;
+            const bool in = i < n;
+            const double x = in ? la[i] : 0.0, y = in ? lo[i] : 0.0;
+            const double ax = __dmul_rn(x, kDeg), oy = __dmul_rn(y, kDeg);
+            const double cx = cos_lat(ax);
+            double cprev = __shfl_up_sync(0xffffffffu, cx, 1);
+            if (lane == 0) cprev = carry_c;
+            carry_c = __shfl_sync(0xffffffffu, cx, 31);
+            if (in) {
+                const double dx = x - mlat, dy = y - mlon;
+                vlat += dx * dx;
+                vlon += dy * dy;
+                const double dc = hav_km(hav_h(ax, oy, cx, am, om, cm));           // haversine(x, y, mlat, mlon)
+                gyr += dc * dc;
+                if (i > 0) {
+                    const double ap = __dmul_rn(la[i - 1], kDeg), op = __dmul_rn(lo[i - 1], kDeg);
+                    path += hav_km(hav_h(ap, op, cprev, ax, oy, cx));              // haversine(p[i-1], p[i])
+                }
+                const double hh = hav_h(ah, oh, ch, ax, oy, cx);                   // haversine_vector(home, points)
+                hmax = fmax(hmax, hh);
+                near += th_home.less(hh) ? 1ull : 0ull;                            // strict <, features.py:83-84
+            }
         }
         vlat = warp_sum(vlat);
         vlon = warp_sum(vlon);
@@ -135,18 +246,23 @@ __global__ void __launch_bounds__(256) location_segments_kernel(
         path = warp_sum(path);
         near = warp_sum(near);
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) dmax = fmax(dmax, __shfl_xor_sync(0xffffffffu, dmax, o));
+        for (int o = 16; o > 0; o >>= 1) hmax = fmax(hmax, __shfl_xor_sync(0xffffffffu, hmax, o));
+        const double dmax = hav_km(hmax);           // the distance is monotone in h: max d = d(max h)
 
         // ---- pass C: stay points (anchor scan, 32 candidates per step) + label entropy on the fly
         const int64_t* tt = t + a;
         int64_t i = 0, n_stay = 0, n_noise = 0;
         double hsum = 0.0;                          // sum over stay labels of p ln p
         while (i < n) {
-            const double alat = la[i], alon = lo[i];
+            const double aa = __dmul_rn(la[i], kDeg), ao = __dmul_rn(lo[i], kDeg), ac = cos_lat(aa);
             int64_t j = i + 1;
             while (j < n) {
                 const int64_t q = j + lane;
-                const bool stop = (q >= n) || (haversine(alat, alon, la[q], lo[q]) > stay_dist);
+                bool stop = q >= n;
+                if (!stop) {
+                    const double aq = __dmul_rn(la[q], kDeg), oq = __dmul_rn(lo[q], kDeg);
+                    stop = th_stay.greater(hav_h(aa, ao, ac, aq, oq, cos_lat(aq)));    // haversine(anchor, p[q]) > stay_dist
+                }
                 const unsigned ball = __ballot_sync(0xffffffffu, stop);
                 if (ball) {
                     j += __ffs(ball) - 1;
