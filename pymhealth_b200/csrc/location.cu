@@ -175,7 +175,7 @@ struct HavThreshold {
 };
 
 // One warp per segment.
-__global__ void __launch_bounds__(256) location_segments_kernel(
+__global__ void __launch_bounds__(256, 4) location_segments_kernel(
     const double* __restrict__ lat, const double* __restrict__ lon, const int64_t* __restrict__ t,
     const int64_t* __restrict__ offs, int64_t n_segments, const double* __restrict__ home, double limit,
     double stay_dist, int64_t stay_min, double* __restrict__ rows, int64_t* __restrict__ labels) {
