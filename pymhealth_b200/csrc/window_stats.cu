@@ -434,8 +434,9 @@ __global__ void __launch_bounds__(kThreads, 3) window_stats_kernel(const StatsPl
                 const double* srcd = q == 0 ? ring.s1 : q == 1 ? ring.s2 : (M4 && q == 2) ? ring.s3 : ring.s4;
                 const float* srcf = (q == nq - 2) ? ring.ll : ring.zc;
                 double run = carry[q];
-                int pslot = (pre_emit + (blocks_done - emitted * g_hop)) % R1;   // prefix slot of block blocks_done
-                if (pslot < 0) pslot += R1;
+                int pslot = pre_emit + (blocks_done - emitted * g_hop);          // prefix slot of block blocks_done
+                while (pslot >= R1) pslot -= R1;                                  // (no integer division in the stage loop)
+                while (pslot < 0) pslot += R1;
                 for (int base = 0; base < d.nblk; base += 32) {
                     const int b = base + lane;
                     double v = 0.0;
@@ -565,8 +566,10 @@ __global__ void __launch_bounds__(kThreads, 3) window_stats_kernel(const StatsPl
                 }
             }
             const int adv = (ready - emitted) * g_hop;       // blocks released (may exceed RB when hop > k)
-            ring_emit = (ring_emit + adv) % P.RB;
-            pre_emit = (pre_emit + adv) % R1;
+            ring_emit += adv;
+            while (ring_emit >= P.RB) ring_emit -= P.RB;
+            pre_emit += adv;
+            while (pre_emit >= R1) pre_emit -= R1;
             emitted = ready;
         }
         // The next iteration writes ring / prefix slots of NEW blocks only after a barrier that every
