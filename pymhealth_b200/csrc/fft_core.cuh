@@ -7,6 +7,7 @@
 // shared table that the CTA fills once with sincospi in float64.
 #pragma once
 #include "common.cuh"
+#include "fft_consts.cuh"
 
 namespace mhb {
 
@@ -20,11 +21,18 @@ struct FftPlan {
 };
 
 // host: factor n into supported radices; false if a prime factor > kMaxPrime remains
-static inline bool fft_plan(int32_t n, FftPlan* p) {
+// `composite`: also use the register-resident composite butterflies 16 / 12 / 10 / 8 / 6 (float32 transforms): fewer
+// passes, i.e. fewer round trips through shared memory (960 = 16 x 12 x 5 instead of 4 x 4 x 4 x 3 x 5)
+static inline bool fft_plan(int32_t n, FftPlan* p, bool composite = false) {
     p->n = n;
     p->n_radices = 0;
     int32_t r = n;
     auto push = [&](int f) { p->radix[p->n_radices++] = f; };
+    if (composite) {
+        const int big[5] = {16, 12, 10, 8, 6};
+        for (int i = 0; i < 5; ++i)
+            while (r % big[i] == 0 && r / big[i] != 2 && r / big[i] != 3) { push(big[i]); r /= big[i]; }
+    }
     while (r % 4 == 0) { push(4); r /= 4; }
     while (r % 2 == 0) { push(2); r /= 2; }
     for (int f = 3; f <= kMaxPrime; f += 2)
@@ -58,6 +66,127 @@ __device__ __forceinline__ void fill_twiddles(Cx<T>* tw, int n, int count, int r
         double s, c;
         sincospi(-2.0 * static_cast<double>(j) / static_cast<double>(n), &s, &c);
         tw[j] = {static_cast<T>(c), static_cast<T>(s)};
+    }
+}
+
+// ---- register-resident butterflies (float32): primes 2 / 3 / 4 / 5 and Cooley-Tukey composites of them
+using Cf = Cx<float>;
+__device__ __forceinline__ void rdft2(Cf* a) {
+    const Cf t = a[1];
+    a[1] = csub(a[0], t);
+    a[0] = cadd(a[0], t);
+}
+__device__ __forceinline__ void rdft3(Cf* a) {
+    const float s = 0.86602540378443864676f;
+    const Cf t1 = cadd(a[1], a[2]);
+    const Cf t2 = {a[0].x - 0.5f * t1.x, a[0].y - 0.5f * t1.y};
+    const Cf t3 = cscale(csub(a[1], a[2]), s);
+    a[0] = cadd(a[0], t1);
+    a[1] = {t2.x + t3.y, t2.y - t3.x};
+    a[2] = {t2.x - t3.y, t2.y + t3.x};
+}
+__device__ __forceinline__ void rdft4(Cf* a) {
+    const Cf t0 = cadd(a[0], a[2]), t1 = csub(a[0], a[2]);
+    const Cf t2 = cadd(a[1], a[3]), t3 = mul_neg_i(csub(a[1], a[3]));
+    a[0] = cadd(t0, t2);
+    a[2] = csub(t0, t2);
+    a[1] = cadd(t1, t3);
+    a[3] = csub(t1, t3);
+}
+__device__ __forceinline__ void rdft5(Cf* a) {
+    const float c1 = 0.30901699437494742410f, c2 = -0.80901699437494742410f;
+    const float s1 = 0.95105651629515357212f, s2 = 0.58778525229247312917f;
+    const Cf p1 = cadd(a[1], a[4]), m1 = csub(a[1], a[4]);
+    const Cf p2 = cadd(a[2], a[3]), m2 = csub(a[2], a[3]);
+    const Cf a0 = a[0];
+    a[0] = {a0.x + p1.x + p2.x, a0.y + p1.y + p2.y};
+    const Cf u1 = {fmaf(c2, p2.x, fmaf(c1, p1.x, a0.x)), fmaf(c2, p2.y, fmaf(c1, p1.y, a0.y))};
+    const Cf u2 = {fmaf(c1, p2.x, fmaf(c2, p1.x, a0.x)), fmaf(c1, p2.y, fmaf(c2, p1.y, a0.y))};
+    const Cf v1 = mul_neg_i(Cf{fmaf(s2, m2.x, s1 * m1.x), fmaf(s2, m2.y, s1 * m1.y)});
+    const Cf v2 = mul_neg_i(Cf{fmaf(-s1, m2.x, s2 * m1.x), fmaf(-s1, m2.y, s2 * m1.y)});
+    a[1] = cadd(u1, v1);
+    a[4] = csub(u1, v1);
+    a[2] = cadd(u2, v2);
+    a[3] = csub(u2, v2);
+}
+template <int R>
+__device__ __forceinline__ Cf rtw(int m);
+template <>
+__device__ __forceinline__ Cf rtw<6>(int m) { return {kCos6[m % 6], kNSin6[m % 6]}; }
+template <>
+__device__ __forceinline__ Cf rtw<8>(int m) { return {kCos8[m % 8], kNSin8[m % 8]}; }
+template <>
+__device__ __forceinline__ Cf rtw<10>(int m) { return {kCos10[m % 10], kNSin10[m % 10]}; }
+template <>
+__device__ __forceinline__ Cf rtw<12>(int m) { return {kCos12[m % 12], kNSin12[m % 12]}; }
+template <>
+__device__ __forceinline__ Cf rtw<16>(int m) { return {kCos16[m % 16], kNSin16[m % 16]}; }
+template <int R>
+__device__ __forceinline__ void rdft_prime(Cf* a);
+template <>
+__device__ __forceinline__ void rdft_prime<2>(Cf* a) { rdft2(a); }
+template <>
+__device__ __forceinline__ void rdft_prime<3>(Cf* a) { rdft3(a); }
+template <>
+__device__ __forceinline__ void rdft_prime<4>(Cf* a) { rdft4(a); }
+template <>
+__device__ __forceinline__ void rdft_prime<5>(Cf* a) { rdft5(a); }
+// R = RA * RB, natural order in and out:
+//   u = RA u2 + u1, t = t2 + RB t1:  y[t] = sum_u1 w_RA^{u1 t1} w_R^{u1 t2} DFT_RB(a[u1::RA])[t2]
+template <int R, int RA, int RB>
+__device__ __forceinline__ void rdft_composite(Cf* a) {
+    Cf f[RA][RB];
+#pragma unroll
+    for (int u1 = 0; u1 < RA; ++u1) {
+#pragma unroll
+        for (int u2 = 0; u2 < RB; ++u2) f[u1][u2] = a[RA * u2 + u1];
+        rdft_prime<RB>(f[u1]);
+#pragma unroll
+        for (int t2 = 1; t2 < RB; ++t2)
+            if (u1 > 0) f[u1][t2] = cmul(f[u1][t2], rtw<R>(u1 * t2));
+    }
+#pragma unroll
+    for (int t2 = 0; t2 < RB; ++t2) {
+        Cf g[RA];
+#pragma unroll
+        for (int u1 = 0; u1 < RA; ++u1) g[u1] = f[u1][t2];
+        rdft_prime<RA>(g);
+#pragma unroll
+        for (int t1 = 0; t1 < RA; ++t1) a[t2 + RB * t1] = g[t1];
+    }
+}
+template <int R>
+__device__ __forceinline__ void rdft(Cf* a);
+template <>
+__device__ __forceinline__ void rdft<6>(Cf* a) { rdft_composite<6, 2, 3>(a); }
+template <>
+__device__ __forceinline__ void rdft<8>(Cf* a) { rdft_composite<8, 2, 4>(a); }
+template <>
+__device__ __forceinline__ void rdft<10>(Cf* a) { rdft_composite<10, 2, 5>(a); }
+template <>
+__device__ __forceinline__ void rdft<12>(Cf* a) { rdft_composite<12, 3, 4>(a); }
+template <>
+__device__ __forceinline__ void rdft<16>(Cf* a) { rdft_composite<16, 4, 4>(a); }
+
+// One Stockham pass of a composite radix (float32): same indexing as stockham_pass below
+template <int R>
+__device__ __forceinline__ void stockham_pass_composite(const Cf* __restrict__ in, Cf* __restrict__ out, int n, int ns,
+                                                        const Cf* __restrict__ tw, int r, int G) {
+    const int nb = n / R;
+    const int tstep = n / (ns * R);
+    for (int j = r; j < nb; j += G) {
+        const int k = j % ns;
+        Cf a[R];
+#pragma unroll
+        for (int t = 0; t < R; ++t) a[t] = in[j + t * nb];
+        if (ns > 1) {
+#pragma unroll
+            for (int t = 1; t < R; ++t) a[t] = cmul(a[t], tw[t * k * tstep]);
+        }
+        rdft<R>(a);
+        const int o = (j - k) * R + k;
+#pragma unroll
+        for (int t = 0; t < R; ++t) out[o + t * ns] = a[t];
     }
 }
 
@@ -153,6 +282,19 @@ __device__ __forceinline__ Cx<T>* stockham_fft(Cx<T>* a, Cx<T>* b, const FftPlan
             case 3: stockham_pass<T, 3>(in, out, plan.n, ns, tw, r, G); break;
             case 4: stockham_pass<T, 4>(in, out, plan.n, ns, tw, r, G); break;
             case 5: stockham_pass<T, 5>(in, out, plan.n, ns, tw, r, G); break;
+            case 6:
+            case 8:
+            case 10:
+            case 12:
+            case 16:
+                if constexpr (sizeof(T) == 4) {            // composite radices exist for float32 plans only
+                    if (R == 6) stockham_pass_composite<6>(in, out, plan.n, ns, tw, r, G);
+                    else if (R == 8) stockham_pass_composite<8>(in, out, plan.n, ns, tw, r, G);
+                    else if (R == 10) stockham_pass_composite<10>(in, out, plan.n, ns, tw, r, G);
+                    else if (R == 12) stockham_pass_composite<12>(in, out, plan.n, ns, tw, r, G);
+                    else stockham_pass_composite<16>(in, out, plan.n, ns, tw, r, G);
+                }
+                break;
             default: stockham_pass_generic<T>(in, out, plan.n, ns, R, tw, r, G); break;
         }
         ns *= R;

@@ -34,7 +34,7 @@ int32_t spectral_batched_try(const float* x, const mhb_windows* geom, int64_t nw
 namespace {
 
 constexpr int kMaxCols = 32;
-constexpr int kWarps = 8;
+constexpr int kWarps = 8;          // at most; large windows run fewer warps per CTA so that several CTAs share an SM
 
 struct SpectralPlan {
     const float* x;
@@ -71,22 +71,50 @@ __global__ void __launch_bounds__(kWarps * 32) window_spectral_kernel(const Spec
     if (P.even) fill_twiddles<float>(tw2, P.W, P.nb, threadIdx.x, blockDim.x);
     __syncthreads();
 
-    for (int64_t w = static_cast<int64_t>(blockIdx.x) * kWarps + warp; w < P.total_windows;
-         w += static_cast<int64_t>(gridDim.x) * kWarps) {
+    const int n_warps = blockDim.x >> 5;
+    for (int64_t w = static_cast<int64_t>(blockIdx.x) * n_warps + warp; w < P.total_windows;
+         w += static_cast<int64_t>(gridDim.x) * n_warps) {
         const int64_t series = w / P.nw;
         const int64_t wi = w - series * P.nw;
         const float* src = P.x + series * P.series_stride + wi * P.S;
 
-        // ---- load, float64 sum (exact DC), mean removal, pack
+        // ---- ONE pass over global memory: stage the raw samples (packed) and take the float64 sum (exact DC);
+        // the mean is then removed in shared memory
         double sum = 0.0;
-        for (int i = lane; i < P.W; i += 32) sum += static_cast<double>(src[i]);
+        if (P.even) {
+            if ((reinterpret_cast<uintptr_t>(src) & 7) == 0) {
+                const float2* s2 = reinterpret_cast<const float2*>(src);
+#pragma unroll 4
+                for (int i = lane; i < N; i += 32) {
+                    const float2 v = s2[i];
+                    A[i] = {v.x, v.y};
+                    sum += static_cast<double>(v.x) + static_cast<double>(v.y);
+                }
+            } else {
+#pragma unroll 4
+                for (int i = lane; i < N; i += 32) {
+                    const float a0 = src[2 * i], a1 = src[2 * i + 1];
+                    A[i] = {a0, a1};
+                    sum += static_cast<double>(a0) + static_cast<double>(a1);
+                }
+            }
+        } else {
+#pragma unroll 4
+            for (int i = lane; i < N; i += 32) {
+                const float a0 = src[i];
+                A[i] = {a0, 0.f};
+                sum += static_cast<double>(a0);
+            }
+        }
         sum = warp_sum(sum);
         const float mean = static_cast<float>(sum / P.W);
         __syncwarp();
         if (P.even) {
-            for (int i = lane; i < N; i += 32) A[i] = {src[2 * i] - mean, src[2 * i + 1] - mean};
+#pragma unroll 4
+            for (int i = lane; i < N; i += 32) A[i] = {A[i].x - mean, A[i].y - mean};
         } else {
-            for (int i = lane; i < N; i += 32) A[i] = {src[i] - mean, 0.f};
+#pragma unroll 4
+            for (int i = lane; i < N; i += 32) A[i].x -= mean;
         }
         __syncwarp();
 
@@ -155,13 +183,24 @@ __global__ void __launch_bounds__(kWarps * 32) window_spectral_kernel(const Spec
                 if (arg == 0x7fffffff) v = CUDART_NAN;                       // empty range
                 else v = kind == MHB_S_PEAK_BIN ? static_cast<double>(arg) : static_cast<double>(arg) * P.bin_hz;
             } else if (kind == MHB_S_ENTROPY) {
+                // bins 1.. in float32 with the fast log2 (absolute error 2^-22 on O(1) arguments); the DC term, which may
+                // be within 1e-7 of 1 on a gravity axis, through log1p in float64
                 const float inv = static_cast<float>(1.0 / tot);
-                float h = 0.f;
-                for (int k = lane; k < P.nb; k += 32) {
-                    const float p = psd[k] * inv + 1e-30f;
-                    h += p * logf(p);
+                float h0 = 0.f, h1 = 0.f;
+                int k = lane == 0 ? 32 : lane;
+                for (; k + 32 < P.nb; k += 64) {
+                    const float p = fmaf(psd[k], inv, 1e-30f), p2 = fmaf(psd[k + 32], inv, 1e-30f);
+                    h0 = fmaf(p, __log2f(p), h0);
+                    h1 = fmaf(p2, __log2f(p2), h1);
                 }
-                v = -warp_sum(static_cast<double>(h));
+                if (k < P.nb) {
+                    const float p = fmaf(psd[k], inv, 1e-30f);
+                    h0 = fmaf(p, __log2f(p), h0);
+                }
+                double hs = warp_sum(static_cast<double>((h0 + h1) * 0.69314718055994530942f));
+                const double p0 = dc / tot + 1e-30, qrest = (tot - dc) / tot;
+                hs += p0 * (qrest < 0.5 ? log1p(-qrest) : log(p0));
+                v = -hs;
             }
             if (lane == 0) put(P, obase + j * P.o_col, v);
         }
@@ -207,7 +246,7 @@ int32_t spectral_launch(const float* x, const mhb_windows* geom, double fs, cons
     P.even = (P.W % 2 == 0) ? 1 : 0;
     P.N = P.even ? P.W / 2 : P.W;
     P.nb = P.W / 2 + 1;
-    MHB_REQUIRE(fft_plan(P.N, &P.fft), MHB_E_UNSUPPORTED,
+    MHB_REQUIRE(fft_plan(P.N, &P.fft, getenv("MHB_FFT_SMALL_RADIX") == nullptr), MHB_E_UNSUPPORTED,
                 "%s: FFT length %d has a prime factor > %d", who, P.N, kMaxPrime);
     P.fs = fs;
     P.bin_hz = rfft_bin_hz(P.W, fs);
@@ -253,17 +292,34 @@ int32_t spectral_launch(const float* x, const mhb_windows* geom, double fs, cons
                                                 o_series, o_window, o_col, stream_v);
         if (st != -100) return st;
     }
-    const size_t smem = sizeof(Cx<float>) * (static_cast<size_t>(P.N) + (P.even ? P.nb : 0) +
-                                             static_cast<size_t>(kWarps) * 2 * P.N);
-    MHB_REQUIRE(smem <= 200 * 1024, MHB_E_UNSUPPORTED, "%s: wsize=%d needs %zu bytes of shared memory", who, P.W, smem);
+    // one warp per window, two N-point buffers per warp: pick the warps per CTA that pack the most warps on an SM
+    const size_t shared_tab = sizeof(Cx<float>) * (static_cast<size_t>(P.N) + (P.even ? P.nb : 0));
+    const size_t per_warp = sizeof(Cx<float>) * 2 * static_cast<size_t>(P.N);
+    MHB_REQUIRE(shared_tab + per_warp <= 200 * 1024, MHB_E_UNSUPPORTED, "%s: wsize=%d needs %zu bytes of shared memory", who,
+                P.W, shared_tab + per_warp);
+    int best_warps = 1, best_total = 0;
+    for (int wv = 1; wv <= kWarps; ++wv) {
+        const size_t sm = shared_tab + per_warp * wv;
+        if (sm > 200 * 1024) break;
+        int per_sm = static_cast<int>((227 * 1024) / (sm + 1024));
+        if (per_sm > 16) per_sm = 16;
+        if (per_sm * wv > 64) per_sm = 64 / wv;
+        if (per_sm * wv >= best_total) {
+            best_total = per_sm * wv;
+            best_warps = wv;
+        }
+    }
+    const size_t smem = shared_tab + per_warp * best_warps;
     cudaError_t e = cudaFuncSetAttribute(window_spectral_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          static_cast<int>(smem));
     if (e != cudaSuccess) return cuda_status(e, who);
-    int64_t ctas = (P.total_windows + kWarps - 1) / kWarps;
-    const int per_sm = static_cast<int>((220 * 1024) / (smem + 1024)) > 0 ? static_cast<int>((220 * 1024) / (smem + 1024)) : 1;
-    const int64_t max_ctas = static_cast<int64_t>(kNumSMs) * (per_sm > 8 ? 8 : per_sm);
+    int64_t ctas = (P.total_windows + best_warps - 1) / best_warps;
+    int per_sm = static_cast<int>((227 * 1024) / (smem + 1024));
+    if (per_sm < 1) per_sm = 1;
+    if (per_sm * best_warps > 64) per_sm = 64 / best_warps;
+    const int64_t max_ctas = static_cast<int64_t>(kNumSMs) * per_sm;
     if (ctas > max_ctas) ctas = max_ctas;
-    window_spectral_kernel<<<static_cast<unsigned>(ctas), kWarps * 32, smem, static_cast<cudaStream_t>(stream_v)>>>(P);
+    window_spectral_kernel<<<static_cast<unsigned>(ctas), best_warps * 32, smem, static_cast<cudaStream_t>(stream_v)>>>(P);
     return cuda_status(cudaGetLastError(), who);
 }
 
