@@ -27,6 +27,9 @@ namespace mhb {
 int32_t spectral_fast_try(const float* x, const mhb_windows* geom, int64_t nw, double bin_hz, const int32_t* cols,
                           const int32_t* lo, const int32_t* hi, int32_t n_cols, void* out, int32_t out_f32,
                           int64_t o_series, int64_t o_window, int64_t o_col, void* stream);
+int32_t spectral_w1920_try(const float* x, const mhb_windows* geom, int64_t nw, double bin_hz, const int32_t* cols,
+                           const int32_t* lo, const int32_t* hi, int32_t n_cols, void* out, int32_t out_f32,
+                           int64_t o_series, int64_t o_window, int64_t o_col, void* stream);
 int32_t spectral_batched_try(const float* x, const mhb_windows* geom, int64_t nw, double bin_hz, const int32_t* cols,
                              const int32_t* lo, const int32_t* hi, int32_t n_cols, void* out, int32_t out_f32,
                              int64_t o_series, int64_t o_window, int64_t o_col, void* stream);
@@ -287,6 +290,9 @@ int32_t spectral_launch(const float* x, const mhb_windows* geom, double fs, cons
             const int32_t sf = spectral_fast_try(x, geom, nw, P.bin_hz, P.col, P.lo, P.hi, n_features, out, out_f32,
                                                  o_series, o_window, o_col, stream_v);
             if (sf != -100) return sf;
+            const int32_t s9 = spectral_w1920_try(x, geom, nw, P.bin_hz, P.col, P.lo, P.hi, n_features, out, out_f32,
+                                                  o_series, o_window, o_col, stream_v);
+            if (s9 != -100) return s9;
         }
         const int32_t st = spectral_batched_try(x, geom, nw, P.bin_hz, P.col, P.lo, P.hi, n_features, out, out_f32,
                                                 o_series, o_window, o_col, stream_v);

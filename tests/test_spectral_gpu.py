@@ -90,6 +90,42 @@ def test_batched_kernel_ragged_batches(n):
         _check_peaks(got[s, :, 2].astype(np.int64), psd_ref, OS.first_index(freqs, 0.3), OS.first_index(freqs, 12.0), "peak")
 
 
+@pytest.mark.parametrize("n", [1920, 1920 + 64 * 3, 1920 + 64 * 4 + 13, 9000, 1920 + 64 * 41])
+def test_w1920_kernel_ragged_batches(n, monkeypatch):
+    """The W=1920/S=64 fast path works on batches of 4 windows: short / ragged last batches, several series, a row
+    stride that defeats TMA, many columns -- against the generic kernel and the oracle."""
+    import torch
+    from oracle import spectral as OS
+    from pymhealth_b200 import engine, synth, spectral as SP
+    x = np.stack([synth.ppg(70 + s, n) + (3.0 if s == 1 else 0.0) for s in range(3)]).astype(np.float32)
+    fs = 64.0
+    feats = [SP.total_power(fs).feature(), SP.band_power(fs, 0.5, 3.0).feature(), SP.band_power(fs, 0.0, 40.0).feature(),
+             SP.relative_band_power(fs, 3.0, 8.0).feature(), SP.peak_bin(fs, 0.3, 12.0).feature(),
+             SP.peak_bin(fs).feature(), SP.spectral_entropy(fs).feature()]
+    xt = torch.from_numpy(x).cuda()
+    got = engine.window_table(xt, 1920, 64, feats, fs=fs, out_dtype=torch.float64).cpu().numpy()
+    wide = torch.zeros((3, n + 3), dtype=torch.float32, device="cuda")        # stride not a multiple of 4 -> no TMA
+    wide[:, :n] = xt
+    got2 = engine.window_table(wide[:, :n], 1920, 64, feats, fs=fs, out_dtype=torch.float64).cpu().numpy()
+    np.testing.assert_array_equal(got, got2)
+    monkeypatch.setenv("MHB_SPECTRAL_GENERIC", "1")
+    gen = engine.window_table(xt, 1920, 64, feats, fs=fs, out_dtype=torch.float64).cpu().numpy()
+    monkeypatch.delenv("MHB_SPECTRAL_GENERIC")
+    for s in range(3):
+        tab = OS.spectral_table(x[s], 1920, 64, fs, [(0.5, 3.0), (0.0, 40.0), (3.0, 8.0)], 0.3, 12.0)
+        tot = tab["total_power"]
+        _check_power(got[s, :, 0], tot, tot, "total")
+        _check_power(got[s, :, 1], tab["band_power_0"], tot, "band 0")
+        _check_power(got[s, :, 2], tab["band_power_1"], tot, "band 1 (includes bin 0)")
+        _check_power(got[s, :, 3], tab["rel_band_power_2"], np.ones_like(tot), "rel band 2")
+        np.testing.assert_allclose(got[s, :, 6], tab["spectral_entropy"], rtol=1e-5)
+        psd_ref, freqs = OS.window_psd(x[s], 1920, 64, fs)
+        _check_peaks(got[s, :, 4].astype(np.int64), psd_ref, OS.first_index(freqs, 0.3), OS.first_index(freqs, 12.0), "peak")
+        _check_peaks(got[s, :, 5].astype(np.int64), psd_ref, 0, len(freqs), "peak all")
+        _check_power(gen[s, :, 0], tot, tot, "generic total")
+        np.testing.assert_allclose(gen[s, :, 6], tab["spectral_entropy"], rtol=1e-5)
+
+
 def test_fft_dropin(ref_spectral):
     from pymhealth_b200 import fft as F
     for case in ("acc", "ppg", "odd"):
