@@ -1,0 +1,100 @@
+"""Size-independent properties at the full sizes of BASELINE configs 4 and 5 (no oracle pass needed)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def test_config4_stats_one_subject_day():
+    """PPG 64 Hz x 24 h (5 529 600 samples), W = 1920, S = 64: 86 371 windows, 30x overlap."""
+    import torch
+    from pymhealth_b200 import synth, engine
+    from pymhealth_b200.generic import stats, timedom
+    n, W, S = 5_529_600, 1920, 64
+    x = synth.ppg(11, n)
+    xd = torch.from_numpy(x).cuda()
+    feats = [stats.mean.feature(), stats.var.feature(), stats.dmin.feature(), stats.dmax.feature(),
+             timedom.zero_crossing_count.feature(0.0), timedom.line_length.feature()]
+    tab = engine.window_table(xd, W, S, feats, out_dtype=torch.float64).cpu().numpy()
+    nw = 1 + (n - W) // S
+    assert tab.shape == (nw, 6)
+    x64 = x.astype(np.float64)
+    cs = np.concatenate([[0.0], np.cumsum(x64)])
+    starts = np.arange(nw) * S
+    np.testing.assert_allclose(tab[:, 0], (cs[starts + W] - cs[starts]) / W, rtol=1e-9, atol=1e-11)       # prefix-sum identity
+    cs2 = np.concatenate([[0.0], np.cumsum(x64 * x64)])
+    var = (cs2[starts + W] - cs2[starts]) / W - tab[:, 0] ** 2
+    np.testing.assert_allclose(tab[:, 1], var, rtol=1e-6, atol=1e-9)
+    # extrema: exact, via block minima (hop 64 blocks, 30 per window)
+    bmin = x[: (n // S) * S].reshape(-1, S).min(axis=1)
+    bmax = x[: (n // S) * S].reshape(-1, S).max(axis=1)
+    k = W // S
+    wmin = np.lib.stride_tricks.sliding_window_view(bmin, k).min(axis=1)[:nw]
+    wmax = np.lib.stride_tricks.sliding_window_view(bmax, k).max(axis=1)[:nw]
+    np.testing.assert_array_equal(tab[:, 2], wmin.astype(np.float64))
+    np.testing.assert_array_equal(tab[:, 3], wmax.astype(np.float64))
+    # zero crossings / line length from prefix sums of the pair terms (pairs inside the window: W - 1 of them)
+    pos = x > 0
+    zc_pair = (pos[1:] != pos[:-1]).astype(np.int64)
+    czc = np.concatenate([[0], np.cumsum(zc_pair)])
+    np.testing.assert_array_equal(tab[:, 4], (czc[starts + W - 1] - czc[starts]).astype(np.float64))
+    ll_pair = np.abs(np.diff(x64))
+    cll = np.concatenate([[0.0], np.cumsum(ll_pair)])
+    np.testing.assert_allclose(tab[:, 5], cll[starts + W - 1] - cll[starts], rtol=1e-5)
+
+
+def test_config4_spectral_parseval_and_shift():
+    """W = 1920 / S = 64 fast path on a long series: Parseval and shift invariance of the window grid."""
+    import torch
+    from pymhealth_b200 import synth, engine, spectral as SP
+    n, W, S, fs = 600_000, 1920, 64, 64.0
+    x = synth.ppg(12, n)
+    xd = torch.from_numpy(x).cuda()
+    feats = [SP.total_power(fs).feature(), SP.peak_bin(fs, 0.5, 4.0).feature(), SP.spectral_entropy(fs).feature()]
+    tab = engine.window_table(xd, W, S, feats, fs=fs, out_dtype=torch.float64).cpu().numpy()
+    nw = 1 + (n - W) // S
+    assert tab.shape == (nw, 3)
+    # Parseval on the one-sided PSD: sum_k c_k |X_k|^2 = W sum x^2 with c_0 = c_{W/2} = 1, c_k = 2; total power counts
+    # every bin once, so  W sum x^2 = 2 total - |X_0|^2 - |X_{W/2}|^2
+    x64 = x.astype(np.float64)
+    cs2 = np.concatenate([[0.0], np.cumsum(x64 * x64)])
+    cs = np.concatenate([[0.0], np.cumsum(x64)])
+    alt = x64 * np.where(np.arange(n) % 2 == 0, 1.0, -1.0)
+    csa = np.concatenate([[0.0], np.cumsum(alt)])
+    starts = np.arange(nw) * S
+    e = W * (cs2[starts + W] - cs2[starts])
+    x0 = cs[starts + W] - cs[starts]
+    xn = csa[starts + W] - csa[starts]                          # S even: the alternating sign pattern is window-invariant
+    total = (e + x0 ** 2 + xn ** 2) / 2
+    np.testing.assert_allclose(tab[:, 0], total, rtol=2e-6)
+    assert np.all((tab[:, 1] >= 15) & (tab[:, 1] < 120))          # bins of 0.5 .. 4 Hz at 1/30 Hz per bin
+    assert np.all((tab[:, 2] > 0) & (tab[:, 2] < np.log(961)))
+    tab2 = engine.window_table(xd[S * 7:], W, S, feats, fs=fs, out_dtype=torch.float64).cpu().numpy()
+    np.testing.assert_array_equal(tab2, tab[7:])                  # same windows, other batches / lanes: bit-identical
+
+
+def test_config5_month_of_1hz_gps():
+    """One subject-month at 1 Hz (2 592 000 points, 30 day segments): kernels agree with each other and with the oracle
+    on two of the days."""
+    from oracle import location as OL
+    from pymhealth_b200 import synth
+    from pymhealth_b200.location import features
+    day, ndays = 86400, 30
+    lat, lon, t, home = synth.gps(9, day * ndays, 1)
+    offs = np.arange(ndays + 1) * day
+    rows = features.segment_rows(lat, lon, t, offs, [home] * ndays, limit=0.1)
+    assert rows.shape == (ndays, 11)
+    assert np.all(rows[:, 0] == day)
+    d = features.arr_successive_distance(lat, lon)
+    assert d[0] == 0.0
+    for k in range(ndays):
+        seg = d[k * day + 1:(k + 1) * day]                        # the step INTO a day belongs to no day
+        np.testing.assert_allclose(rows[k, 1], seg.sum(), rtol=1e-9)
+    dh = features.arr_distance_from_home(lat, lon, home)
+    np.testing.assert_array_equal(rows[:, 5], (dh.reshape(ndays, day) < 0.1).sum(axis=1).astype(np.float64))   # counts: exact
+    np.testing.assert_allclose(rows[:, 4], dh.reshape(ndays, day).max(axis=1), rtol=1e-12)
+    assert np.all((rows[:, 6] >= 0) & (rows[:, 6] <= 1))
+    for k in (0, 17):
+        sl = slice(k * day, (k + 1) * day)
+        np.testing.assert_allclose(d[sl][1:], OL.arr_successive_distance(lat[sl], lon[sl])[1:], rtol=1e-9, atol=1e-12)
+        np.testing.assert_allclose(rows[k, 2], OL.arr_location_variance(lat[sl], lon[sl]), rtol=1e-9)
