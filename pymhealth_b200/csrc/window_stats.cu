@@ -711,14 +711,16 @@ int32_t window_stats_impl(const InT* x, const mhb_windows* geom, const int32_t* 
     // deferred finalisation: let about half a CTA of windows pile up before phase 3 runs
     {
         const int64_t per_stage = P.TB / P.hop + 1;
-        int64_t flush = kThreads / 2 - per_stage;
+        // heavily overlapping windows (k > kDirectK: one finished window per block) finalize in bigger groups
+        int64_t flush = (P.k > kDirectK ? (3 * kThreads) / 4 : kThreads / 2) - per_stage;
         const int64_t cap = (1536 - P.k - P.TB) / P.hop - per_stage - 1;   // keep the ring <= 1536 blocks
         if (flush > cap) flush = cap;
         if (flush < 1) flush = 1;
         P.flush = static_cast<int32_t>(flush);
         P.RB = static_cast<int32_t>((flush + per_stage + 1) * P.hop + P.k + P.TB + 1);
     }
-    P.NS = 2;
+    // ... and trade the second stage buffer for the longer ring (the other CTAs of the SM cover the copy latency)
+    P.NS = P.k > kDirectK ? 1 : 2;
     constexpr int A = 16 / sizeof(InT);
     P.stage_elems = ((P.TB * P.g + 1 + (A - 1) + A - 1) / A) * A + A;
     P.use_tma = (reinterpret_cast<uintptr_t>(x) % 16 == 0) ? 1 : 0;
