@@ -177,15 +177,7 @@ __global__ void __launch_bounds__(kT, 3) spectral_w1920_kernel(const Plan1920 P)
             advance(s2, b2);
             if (s2 < n_series) issue(s2, b2, slot ^ 1);
         }
-        // ---- pivot of every window: 32 samples spread over the window (any value near the mean works, bin 0 is
-        // restored exactly in pass B)
         if (tma_ok(goff, n_load) == false) __syncthreads();       // cooperative copy visible
-        if (warp < kBW) {
-            float m = warp < nwin ? tile[warp * kS + 60 * lane] : 0.f;
-            m = warp_sum(m) * (1.0f / 32.0f);
-            if (lane == 0) piv[warp] = m;
-        }
-        __syncthreads();
 
         // ---- pass A1: 8-point DFTs; item (w, b, n2), n2 fastest so that a warp reads consecutive float2
 #pragma unroll 1
@@ -193,8 +185,20 @@ __global__ void __launch_bounds__(kT, 3) spectral_w1920_kernel(const Plan1920 P)
             const int w = it / 120, r = it - w * 120;
             if (w >= nwin) continue;
             const int b = r / 10, n2 = r - b * 10;
-            const float mh = -0.5f * piv[w];
-            const float2* z = reinterpret_cast<const float2*>(tile + w * kS) + 10 * b + n2;
+            // pivot of the window: the mean of 16 samples spread over it (z[120 a], a = 0..7).  Every thread of the
+            // window reads the same addresses (broadcasts), so all agree bit for bit; any value near the mean works,
+            // bin 0 is restored exactly in pass B.
+            const float2* zw = reinterpret_cast<const float2*>(tile + w * kS);
+            float m = 0.f;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const float2 v = zw[120 * q];
+                m += v.x + v.y;
+            }
+            m *= (1.0f / 16.0f);
+            if (r == 0) piv[w] = m;
+            const float mh = -0.5f * m;
+            const float2* z = zw + 10 * b + n2;
             C a[8];
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
