@@ -143,6 +143,18 @@ def window_table(x, wsize, wstep, features, zc_threshold=0.0, fs=1.0, out_dtype=
     return out[0] if was_1d else out
 
 
+def n_index_windows(first, last, wstep, is_float):
+    """len(np.arange(first, last, wstep)) without building the array (util/windows.py:175): numpy takes
+    ceil((stop - start) / step) in float64 for floats and the exact integer count for integers."""
+    if is_float:
+        if not wstep > 0:
+            raise ValueError("get_indices: wstep must be > 0")
+        return max(0, int(math.ceil((float(last) - float(first)) / float(wstep))))
+    if int(wstep) <= 0:
+        raise ValueError("get_indices: wstep must be > 0")
+    return len(range(int(first), int(last), int(wstep)))
+
+
 def device_get_indices(index, wsize, wstep):
     """get_indices (util/windows.py:162-178) on the device -> int64 cuda tensor [2, n_windows].
 
@@ -183,14 +195,9 @@ def device_get_indices(index, wsize, wstep):
     is_f = it.dtype == torch.float64
     if is_f:
         wsize, wstep = float(wsize), float(wstep)
-        if not wstep > 0:
-            raise ValueError("get_indices: wstep must be > 0")
-        nwin = max(0, int(math.ceil((last - first) / wstep)))       # len(np.arange(first, last, wstep))
     else:
         wsize, wstep = int(wsize), int(wstep)
-        if wstep <= 0:
-            raise ValueError("get_indices: wstep must be > 0")
-        nwin = len(range(first, last, wstep))
+    nwin = n_index_windows(first, last, wstep, is_f)
     out = torch.empty((2, nwin), dtype=torch.int64, device=it.device)
     if nwin:
         fn = lib.mhb_get_indices_f64 if is_f else lib.mhb_get_indices_i64
