@@ -126,6 +126,26 @@ def test_w1920_kernel_ragged_batches(n, monkeypatch):
         np.testing.assert_allclose(gen[s, :, 6], tab["spectral_entropy"], rtol=1e-5)
 
 
+@pytest.mark.parametrize("W,S", [(36, 9), (64, 16), (90, 30), (96, 32), (100, 50), (120, 40), (128, 64), (256, 128), (384, 96),
+                                 (1000, 500), (1024, 512), (75, 25)])
+def test_generic_kernel_window_lengths(W, S):
+    """The generic warp-per-window kernel over window lengths that exercise every register radix of the planner
+    (16 / 12 / 10 / 8 / 6 composites, 5 / 4 / 3 / 2, odd W) against the oracle."""
+    from oracle import spectral as OS
+    from pymhealth_b200 import synth, spectral as SP
+    from pymhealth_b200.util import rolling_apply
+    fs = 50.0
+    x = synth.accelerometer(90 + W, 6 * W + 17)[2]
+    got = rolling_apply({"total": SP.total_power(fs), "bp": SP.band_power(fs, 1.0, 6.0), "pk": SP.peak_bin(fs, 0.5, 12.0),
+                         "h": SP.spectral_entropy(fs)})(x, W, S)
+    tab = OS.spectral_table(x, W, S, fs, [(1.0, 6.0)], 0.5, 12.0)
+    _check_power(got["total"], tab["total_power"], tab["total_power"], "total W=%d" % W)
+    _check_power(got["bp"], tab["band_power_0"], tab["total_power"], "band W=%d" % W)
+    np.testing.assert_allclose(got["h"], tab["spectral_entropy"], rtol=1e-5)
+    psd_ref, freqs = OS.window_psd(x, W, S, fs)
+    _check_peaks(got["pk"].astype(np.int64), psd_ref, OS.first_index(freqs, 0.5), OS.first_index(freqs, 12.0), "peak W=%d" % W)
+
+
 def test_fft_dropin(ref_spectral):
     from pymhealth_b200 import fft as F
     for case in ("acc", "ppg", "odd"):
