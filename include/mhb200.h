@@ -195,6 +195,11 @@ int64_t mhb_diff_stats_workspace(int64_t n_diff);
 int32_t mhb_diff_stats_f64(const double* x, int64_t n, double abs_threshold, double* workspace, int64_t workspace_len,
                            double* out6, void* stream);
 
+/* timedom.gradient(x) (src/mhealth/generic/timedom.py:11-31) -> float64 [n] (differences in the input type);
+ * timedom.zero_crossings(x, th) (:34-49) -> n - 1 flags, one byte each. */
+int32_t mhb_gradient(int32_t is_f64, const void* x, int64_t n, double* out, void* stream);
+int32_t mhb_zero_crossings(int32_t is_f64, const void* x, int64_t n, double threshold, uint8_t* out, void* stream);
+
 /* ppg.slope_sum(x, w) (src/mhealth/heart/ppg.py:28-42): out[i] = sum(diff(x)[i-w : i]) for w <= i < n - 1, else 0;
  * float64 [n] out whatever the input type. */
 int32_t mhb_slope_sum(int32_t is_f64, const void* x, int64_t n, int32_t w, double* out, void* stream);

@@ -76,6 +76,8 @@ SIGNATURES = {
     "mhb_accel_magnitude_dot": (C.c_int32, [C.c_int32, _vp, _vp, _vp, C.c_int64, _vp, C.c_int64, _vp, _vp]),
     "mhb_diff_stats_workspace": (C.c_int64, [C.c_int64]),
     "mhb_diff_stats_f64": (C.c_int32, [_vp, C.c_int64, C.c_double, _vp, C.c_int64, _vp, _vp]),
+    "mhb_gradient": (C.c_int32, [C.c_int32, _vp, C.c_int64, _vp, _vp]),
+    "mhb_zero_crossings": (C.c_int32, [C.c_int32, _vp, C.c_int64, C.c_double, _vp, _vp]),
     "mhb_slope_sum": (C.c_int32, [C.c_int32, _vp, C.c_int64, C.c_int32, _vp, _vp]),
     "mhb_haversine_elementwise": (C.c_int32, [_vp, _vp, _vp, _vp, C.c_int64, _vp, _vp]),
     "mhb_haversine_vector": (C.c_int32, [C.c_double, C.c_double, _vp, _vp, C.c_int64, _vp, _vp]),

@@ -88,8 +88,67 @@ __global__ void __launch_bounds__(256) slope_sum_kernel(const T* __restrict__ x,
     }
 }
 
+// timedom.gradient (src/mhealth/generic/timedom.py:11-31): out[0] = x[1] - x[0], out[n-1] = x[n-1] - x[n-2],
+// out[i] = (x[i+1] - x[i-1]) / 2; the difference is formed in the input type (float32 input: float32 subtraction), the
+// result is float64.
+template <typename T>
+__global__ void __launch_bounds__(256) gradient_kernel(const T* __restrict__ x, int64_t n, double* __restrict__ out) {
+    const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+        double v;
+        if (i == 0) v = static_cast<double>(x[1] - x[0]);
+        else if (i == n - 1) v = static_cast<double>(x[n - 1] - x[n - 2]);
+        else v = static_cast<double>(x[i + 1] - x[i - 1]) / 2;
+        out[i] = v;
+    }
+}
+
+// timedom.zero_crossings (timedom.py:34-49): samples with |x| <= th count as zero, pos = x > 0, out[i] = pos[i] xor
+// pos[i+1] (n - 1 flags, one byte each).
+template <typename T>
+__global__ void __launch_bounds__(256) zero_crossings_kernel(const T* __restrict__ x, int64_t n, double th,
+                                                             uint8_t* __restrict__ out) {
+    const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n - 1; i += stride) {
+        const double a = static_cast<double>(x[i]), b = static_cast<double>(x[i + 1]);
+        const bool pa = a > 0.0 && !(fabs(a) <= th), pb = b > 0.0 && !(fabs(b) <= th);
+        out[i] = pa != pb ? 1 : 0;
+    }
+}
+
+static int64_t grid_1d(int64_t n) {
+    int64_t blocks = (n + 255) / 256;
+    const int64_t cap = static_cast<int64_t>(kNumSMs) * 16;
+    if (blocks > cap) blocks = cap;
+    return blocks < 1 ? 1 : blocks;
+}
+
 }  // namespace
 }  // namespace mhb
+
+extern "C" int32_t mhb_gradient(int32_t is_f64, const void* x, int64_t n, double* out, void* stream) {
+    using namespace mhb;
+    MHB_REQUIRE(n >= 2, MHB_E_ARG, "gradient: at least two samples are needed (n = %lld)", static_cast<long long>(n));
+    MHB_REQUIRE(x && out, MHB_E_ARG, "gradient: null pointer");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const unsigned blocks = static_cast<unsigned>(grid_1d(n));
+    if (is_f64) gradient_kernel<double><<<blocks, 256, 0, s>>>(static_cast<const double*>(x), n, out);
+    else gradient_kernel<float><<<blocks, 256, 0, s>>>(static_cast<const float*>(x), n, out);
+    return cuda_status(cudaGetLastError(), "gradient launch");
+}
+
+extern "C" int32_t mhb_zero_crossings(int32_t is_f64, const void* x, int64_t n, double threshold, uint8_t* out,
+                                      void* stream) {
+    using namespace mhb;
+    MHB_REQUIRE(n >= 0, MHB_E_ARG, "zero_crossings: negative size");
+    if (n < 2) return MHB_OK;
+    MHB_REQUIRE(x && out, MHB_E_ARG, "zero_crossings: null pointer");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const unsigned blocks = static_cast<unsigned>(grid_1d(n - 1));
+    if (is_f64) zero_crossings_kernel<double><<<blocks, 256, 0, s>>>(static_cast<const double*>(x), n, threshold, out);
+    else zero_crossings_kernel<float><<<blocks, 256, 0, s>>>(static_cast<const float*>(x), n, threshold, out);
+    return cuda_status(cudaGetLastError(), "zero_crossings launch");
+}
 
 extern "C" int32_t mhb_slope_sum(int32_t is_f64, const void* x, int64_t n, int32_t w, double* out, void* stream) {
     using namespace mhb;

@@ -21,3 +21,40 @@ def hjorth_parameters(x):
     a = np.asarray(x).ravel()
     v = _one_window(a, [hjorth_activity.feature(), hjorth_mobility.feature(), hjorth_complexity.feature()])
     return (float(v[0]), float(v[1]), float(v[2]))
+
+
+def _series(x):
+    from ..engine import require_cuda
+    torch = require_cuda()
+    a = np.asarray(x)
+    if a.ndim != 1:
+        raise ValueError("1-D array expected")
+    if a.dtype not in (np.float32, np.float64):
+        a = a.astype(np.float64)
+    return torch, torch.from_numpy(np.array(a, order="C", copy=True)).cuda()
+
+
+def gradient(x):
+    """Derivative of the input: halved distance between x[i-1] and x[i+1], one-sided at the ends; float64 output,
+    differences in the input type (timedom.py:11-31)."""
+    from ..engine import _stream_ptr
+    torch, t = _series(x)
+    n = t.shape[0]
+    if n < 2:
+        raise ValueError("gradient needs at least two samples")
+    out = torch.empty(n, dtype=torch.float64, device=t.device)
+    L.check(L.load().mhb_gradient(1 if t.dtype == torch.float64 else 0, t.data_ptr(), n, out.data_ptr(), _stream_ptr(torch)),
+            "gradient")
+    return out.cpu().numpy()
+
+
+def zero_crossings(x, th=0):
+    """Boolean array: was there a zero crossing between samples i and i + 1, after zeroing |x| <= th
+    (timedom.py:34-49)."""
+    from ..engine import _stream_ptr
+    torch, t = _series(x)
+    n = t.shape[0]
+    out = torch.zeros(max(0, n - 1), dtype=torch.uint8, device=t.device)
+    L.check(L.load().mhb_zero_crossings(1 if t.dtype == torch.float64 else 0, t.data_ptr(), n, float(th), out.data_ptr(),
+                                        _stream_ptr(torch)), "zero_crossings")
+    return out.cpu().numpy().astype(bool)

@@ -243,6 +243,12 @@ def extra_fixture():
     out["hrv/ssd"] = np.array(hrv.ssd(rr))
     out["hrv/sdsd"] = np.array(hrv.sdsd(rr))
     out["hrv/nni_to_ms"] = hrv.nni_to_ms(rr[:16] * 1e6, 'ns')
+    g = a64[2][:2001].copy()
+    out["td/x"] = g
+    out["td/gradient_f64"] = timedom.gradient(g)
+    out["td/gradient_f32"] = timedom.gradient(g.astype(np.float32))
+    out["td/zero_crossings_0"] = timedom.zero_crossings(g - g.mean(), 0.0)
+    out["td/zero_crossings_th"] = timedom.zero_crossings(g - g.mean(), 0.05)
     from mhealth.heart import ppg as rppg
     sig = synth.ppg(3, 4000).astype(np.float64)
     out["ppg/x"] = sig

@@ -120,3 +120,22 @@ def test_ppg_slope_sum(ref_extra):
     np.testing.assert_allclose(got32, ref_extra["ppg/slope_sum_9"], rtol=0, atol=1e-6 * np.abs(x).max())
     assert ppg.slope_sum(np.zeros(0), 3).shape == (0,)
     assert np.all(ppg.slope_sum(np.arange(5.0), 9) == 0)           # window longer than the signal
+
+
+def test_gradient_and_zero_crossings(ref_extra):
+    from pymhealth_b200.generic import timedom
+    g = ref_extra["td/x"]
+    np.testing.assert_array_equal(timedom.gradient(g), ref_extra["td/gradient_f64"])          # same operations: exact
+    got32 = timedom.gradient(g.astype(np.float32))
+    assert got32.dtype == np.float64
+    np.testing.assert_array_equal(got32, ref_extra["td/gradient_f32"])                         # float32 differences
+    c = g - g.mean()
+    z0, zt = timedom.zero_crossings(c, 0.0), timedom.zero_crossings(c, 0.05)
+    assert z0.dtype == bool and z0.shape == (len(g) - 1,)
+    np.testing.assert_array_equal(z0, ref_extra["td/zero_crossings_0"])
+    np.testing.assert_array_equal(zt, ref_extra["td/zero_crossings_th"])
+    assert int(z0.sum()) == timedom.zero_crossing_count(c, 0.0)
+    assert int(zt.sum()) == timedom.zero_crossing_count(c, 0.05)
+    np.testing.assert_array_equal(timedom.gradient(np.array([1.0, 4.0])), [3.0, 3.0])
+    with pytest.raises(ValueError):
+        timedom.gradient(np.array([1.0]))
