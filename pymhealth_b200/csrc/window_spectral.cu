@@ -30,10 +30,6 @@ int32_t spectral_fast_try(const float* x, const mhb_windows* geom, int64_t nw, d
 int32_t spectral_w1920_try(const float* x, const mhb_windows* geom, int64_t nw, double bin_hz, const int32_t* cols,
                            const int32_t* lo, const int32_t* hi, int32_t n_cols, void* out, int32_t out_f32,
                            int64_t o_series, int64_t o_window, int64_t o_col, void* stream);
-int32_t spectral_batched_try(const float* x, const mhb_windows* geom, int64_t nw, double bin_hz, const int32_t* cols,
-                             const int32_t* lo, const int32_t* hi, int32_t n_cols, void* out, int32_t out_f32,
-                             int64_t o_series, int64_t o_window, int64_t o_col, void* stream);
-
 namespace {
 
 constexpr int kMaxCols = 32;
@@ -284,19 +280,14 @@ int32_t spectral_launch(const float* x, const mhb_windows* geom, double fs, cons
         }
     }
     if (n_features > 0 && getenv("MHB_SPECTRAL_GENERIC") == nullptr) {
-        // thread-resident two-pass kernel for W = 500 / S = 250 (spectral_fast.cu); MHB_SPECTRAL_BATCHED selects the
-        // older three-pass batched kernel (spectral_batched.cu) for A/B comparisons
-        if (getenv("MHB_SPECTRAL_BATCHED") == nullptr) {
-            const int32_t sf = spectral_fast_try(x, geom, nw, P.bin_hz, P.col, P.lo, P.hi, n_features, out, out_f32,
-                                                 o_series, o_window, o_col, stream_v);
-            if (sf != -100) return sf;
-            const int32_t s9 = spectral_w1920_try(x, geom, nw, P.bin_hz, P.col, P.lo, P.hi, n_features, out, out_f32,
-                                                  o_series, o_window, o_col, stream_v);
-            if (s9 != -100) return s9;
-        }
-        const int32_t st = spectral_batched_try(x, geom, nw, P.bin_hz, P.col, P.lo, P.hi, n_features, out, out_f32,
-                                                o_series, o_window, o_col, stream_v);
-        if (st != -100) return st;
+        // thread-resident fast paths: W = 500 / S = 250 (spectral_fast.cu) and W = 1920 / S = 64 (spectral_w1920.cu);
+        // MHB_SPECTRAL_GENERIC forces the generic kernel below (tests compare the two)
+        const int32_t sf = spectral_fast_try(x, geom, nw, P.bin_hz, P.col, P.lo, P.hi, n_features, out, out_f32,
+                                             o_series, o_window, o_col, stream_v);
+        if (sf != -100) return sf;
+        const int32_t s9 = spectral_w1920_try(x, geom, nw, P.bin_hz, P.col, P.lo, P.hi, n_features, out, out_f32,
+                                              o_series, o_window, o_col, stream_v);
+        if (s9 != -100) return s9;
     }
     // one warp per window, two N-point buffers per warp: pick the warps per CTA that pack the most warps on an SM
     const size_t shared_tab = sizeof(Cx<float>) * (static_cast<size_t>(P.N) + (P.even ? P.nb : 0));
