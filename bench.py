@@ -272,6 +272,7 @@ def run_b200_arm(args):
 
     # ---- end-to-end through the public host-buffer API (pinned host inputs, H2D + kernels + D2H per step)
     e2e_sub = min(args.e2e_subjects, nsub)
+    numa_node = sharded.bind_host_to_device_numa(local)        # pinned buffers next to this GPU's PCIe root
     hx = torch.empty((e2e_sub * 3, n), dtype=torch.float32).pin_memory()
     hx.copy_(x[:e2e_sub * 3])
     hout = torch.empty((e2e_sub * 3, nw, nf), dtype=torch.float32).pin_memory()
@@ -344,7 +345,8 @@ def run_b200_arm(args):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(hx.numel() * 4),
                     "d2h_bytes_per_step": int(hout.numel() * 4), "subjects_per_step_per_gpu": e2e_sub,
                     "ms_per_step": float(e2e_ms.cpu()) / e2e_steps, "matches_resident_run": check_ok,
-                    "api": "pymhealth_b200.pipeline.FeaturePipeline.run (pinned host in, pinned host out)"},
+                    "api": "pymhealth_b200.pipeline.FeaturePipeline.run (pinned host in, pinned host out)",
+                    "host_numa_node_rank0": numa_node},
             "gpu_launches": 2 * args.steps,
             "clocks": clocks,
             "gather_ms": gather_ms,
