@@ -11,7 +11,7 @@
 // Windows are arbitrary [start, end) index pairs (overlapping, unordered, empty), so there is no block
 // sharing to exploit: one warp owns one window, lanes stride over its samples with float64 shifted power
 // sums (pivot = the window's first sample), and the 32 partial records are combined with warp shuffles in a
-// fixed order (deterministic).  Windows longer than kCtaWindow samples are reduced by a whole CTA.
+// fixed order (deterministic).
 #include <math_constants.h>
 
 #include "common.cuh"
@@ -154,21 +154,18 @@ __device__ __forceinline__ void seg_bounds(const SegPlan& P, int64_t w, int64_t&
     if (e < s) e = s;
 }
 
-constexpr int64_t kCtaWindow = 16384;     // longer windows are reduced by a whole CTA
-
 template <typename InT, typename OutT>
 __global__ void __launch_bounds__(kSegThreads) segment_stats_kernel(const SegPlan P) {
     const InT* x = reinterpret_cast<const InT*>(P.x);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     constexpr int WPC = kSegThreads / 32;
-    __shared__ SegAcc part[WPC];
-    // pass 1: short windows, one per warp
+    // one window per warp, whatever its length: the windows of a call are independent units of very different
+    // sizes (a 5-minute RR segment, a day of 1 Hz GPS), and a grid-stride loop over warps balances them
     for (int64_t w = static_cast<int64_t>(blockIdx.x) * WPC + warp; w < P.n_windows;
          w += static_cast<int64_t>(gridDim.x) * WPC) {
         int64_t s, e;
         seg_bounds(P, w, s, e);
         const int64_t len = e - s;
-        if (len > kCtaWindow) continue;
         const bool valid = len >= P.min_len && len > 0;
         SegAcc a;
         double c = 0.0;
@@ -182,31 +179,6 @@ __global__ void __launch_bounds__(kSegThreads) segment_stats_kernel(const SegPla
             }
         }
         if (lane == 0) seg_emit<OutT>(P, w, len, a, c, valid);
-    }
-    // pass 2: long windows, one per CTA
-    for (int64_t w = blockIdx.x; w < P.n_windows; w += gridDim.x) {
-        int64_t s, e;
-        seg_bounds(P, w, s, e);
-        const int64_t len = e - s;
-        if (len <= kCtaWindow) continue;
-        const bool valid = len >= P.min_len;
-        SegAcc a;
-        double c = 0.0;
-        if (valid) {
-            c = static_cast<double>(x[s]);
-            a = seg_scan<InT>(x, s, e, threadIdx.x, kSegThreads, c, P.th);
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                const SegAcc b = seg_shfl_down(a, o);
-                seg_merge(a, b);
-            }
-            __syncthreads();
-            if (lane == 0) part[warp] = a;
-            __syncthreads();
-            if (threadIdx.x == 0)
-                for (int i = 1; i < WPC; ++i) seg_merge(a, part[i]);
-        }
-        if (threadIdx.x == 0) seg_emit<OutT>(P, w, len, a, c, valid);
     }
 }
 

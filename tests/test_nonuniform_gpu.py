@@ -99,8 +99,8 @@ def test_float_index_and_unsupported():
         nonuniform_rolling_apply(lambda w: w.sum())
 
 
-def test_long_windows_cta_path():
-    """Windows above 16 384 samples are reduced by a whole CTA (a day of 1 Hz GPS = 86 400 samples)."""
+def test_long_windows():
+    """Day-long windows of a 1 Hz series (86 400 samples each)."""
     from oracle import windows as OW
     from pymhealth_b200.util.windows import nonuniform_rolling_apply
     rng = np.random.default_rng(11)
