@@ -13,11 +13,17 @@
 //   rank = 1 + (n-1) q/100, f = floor(rank), m = rank - f, val = lower (1-m) + upper m,
 // q = 0 / 100 short-circuit to min / max; median of an even window is (a+b)/2; mode reproduces the
 // reference's run counter including its first-run quirk (stats.py:81-93).
+#include <cstdlib>
 #include <math_constants.h>
 
 #include "common.cuh"
 
 namespace mhb {
+
+// window_order_blocks.cu: sort every block once + k-way selection (order statistics only); -100 = not covered
+template <typename InT>
+int32_t window_order_blocks_try(const InT* x, const mhb_windows* geom, int64_t nw, const int32_t* h_features,
+                                const double* h_params, int32_t n_features, const mhb_table* table, void* stream_v);
 
 namespace {
 
@@ -253,6 +259,10 @@ int32_t window_order_impl(const InT* x, const mhb_windows* geom, const int32_t* 
         } else {
             P.need_sort = 1;
         }
+    }
+    if (getenv("MHB_ORDER_FULLSORT") == nullptr) {
+        const int32_t st = window_order_blocks_try<InT>(x, geom, nw, h_features, h_params, n_features, table, stream_v);
+        if (st != -100) return st;
     }
     P.n_features = n_features;
     P.x = x;
