@@ -17,6 +17,7 @@
 #include <math_constants.h>
 
 #include "common.cuh"
+#include "sort_regs.cuh"
 
 namespace mhb {
 
@@ -190,7 +191,17 @@ __global__ void __launch_bounds__(256) window_order_kernel(const OrderPlan P) {
             cpx = sqrt(v2 / v1) / mob;                          // timedom.py:149-151
         }
 
-        if (P.need_sort) {
+        if (P.need_sort && G == 32 && p2w >= 32 && p2w <= 512) {
+            // a warp sorts up to 512 elements in registers (shuffles across lanes), then puts them back
+            switch (p2w) {
+                case 32: sort_smem_via_regs<InT, 1>(buf, r); break;
+                case 64: sort_smem_via_regs<InT, 2>(buf, r); break;
+                case 128: sort_smem_via_regs<InT, 4>(buf, r); break;
+                case 256: sort_smem_via_regs<InT, 8>(buf, r); break;
+                default: sort_smem_via_regs<InT, 16>(buf, r); break;
+            }
+            Group<G>::sync();
+        } else if (P.need_sort) {
             for (int k2 = 2; k2 <= p2w; k2 <<= 1) {
                 for (int j = k2 >> 1; j > 0; j >>= 1) {
                     for (int t = r; t < (p2w >> 1); t += G) {

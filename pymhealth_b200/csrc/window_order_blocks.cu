@@ -17,6 +17,7 @@
 #include <math_constants.h>
 
 #include "common.cuh"
+#include "sort_regs.cuh"
 
 namespace mhb {
 
@@ -141,8 +142,21 @@ __device__ __forceinline__ void merge_pair(const T* __restrict__ A, const T* __r
 }
 
 // MERGE: k <= 2 (merge-path selection, a thread per window and column); otherwise k-way bisection (a warp per window)
+template <typename T, int EPL>
+__device__ __forceinline__ void sort_block_regs(const T* __restrict__ src, T* __restrict__ dst, int g, int lane) {
+    T v[EPL];
+#pragma unroll
+    for (int i = 0; i < EPL; ++i) {
+        const int e = lane * EPL + i;
+        v[i] = e < g ? src[e] : Key<T>::inf();
+    }
+    warp_sort_regs<T, EPL>(v, lane);
+#pragma unroll
+    for (int i = 0; i < EPL; ++i) dst[lane * EPL + i] = v[i];
+}
+
 template <typename InT, typename OutT, bool MERGE>
-__global__ void __launch_bounds__(kThreadsOB) window_order_blocks_kernel(const BlocksPlan P) {
+__global__ void __launch_bounds__(kThreadsOB, 4) window_order_blocks_kernel(const BlocksPlan P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     InT* sorted = reinterpret_cast<InT*>(smem_raw);                      // [NB][P2g]
     const InT* xg = reinterpret_cast<const InT*>(P.x);
@@ -162,6 +176,16 @@ __global__ void __launch_bounds__(kThreadsOB) window_order_blocks_kernel(const B
         for (int blk = warp; blk < nblk; blk += kWarpsOB) {
             InT* buf = sorted + static_cast<size_t>(blk) * P2;
             const InT* src = src0 + static_cast<int64_t>(blk) * g;
+            if (P2 <= 512) {                       // register-resident network (<= 16 elements per lane)
+                switch (P2) {
+                    case 32: sort_block_regs<InT, 1>(src, buf, g, lane); break;
+                    case 64: sort_block_regs<InT, 2>(src, buf, g, lane); break;
+                    case 128: sort_block_regs<InT, 4>(src, buf, g, lane); break;
+                    case 256: sort_block_regs<InT, 8>(src, buf, g, lane); break;
+                    default: sort_block_regs<InT, 16>(src, buf, g, lane); break;
+                }
+                continue;
+            }
             for (int i = lane; i < P2; i += 32) buf[i] = i < g ? src[i] : Key<InT>::inf();
             __syncwarp();
             for (int k2 = 2; k2 <= P2; k2 <<= 1) {
@@ -300,7 +324,7 @@ int32_t window_order_blocks_try(const InT* x, const mhb_windows* geom, int64_t n
         for (int j = 0; j < n_features; ++j) n_sel += h_features[j] == MHB_F_IQR ? 2 : 1;
         if (n_sel > 3) return -100;
     }
-    int64_t p2 = 16;
+    int64_t p2 = 32;
     while (p2 < g) p2 <<= 1;
     const int64_t block_bytes = p2 * static_cast<int64_t>(sizeof(InT));
     const int64_t nb_max = (32 * 1024) / block_bytes;
