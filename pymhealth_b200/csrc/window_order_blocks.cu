@@ -158,10 +158,11 @@ __device__ __forceinline__ void sort_block_regs(const T* __restrict__ src, T* __
 template <typename InT, typename OutT, bool MERGE>
 __global__ void __launch_bounds__(kThreadsOB, 4) window_order_blocks_kernel(const BlocksPlan P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    InT* sorted = reinterpret_cast<InT*>(smem_raw);                      // [NB][P2g]
+    InT* sorted = reinterpret_cast<InT*>(smem_raw);                      // [NB][P2g + 1]
     const InT* xg = reinterpret_cast<const InT*>(P.x);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int P2 = P.P2g, g = P.g, n = P.W;
+    const int BS = P2 + 1;       // block stride: odd, so that lanes probing the same position of different blocks do not collide
 
     for (int64_t b = blockIdx.x; b < P.total_batches; b += gridDim.x) {
         const int64_t series = b / P.batches_per_series;
@@ -174,7 +175,7 @@ __global__ void __launch_bounds__(kThreadsOB, 4) window_order_blocks_kernel(cons
         __syncthreads();                                                  // previous batch's selections are done
         // ---- phase 1: stage and sort every block of the batch, one warp per block
         for (int blk = warp; blk < nblk; blk += kWarpsOB) {
-            InT* buf = sorted + static_cast<size_t>(blk) * P2;
+            InT* buf = sorted + static_cast<size_t>(blk) * BS;
             const InT* src = src0 + static_cast<int64_t>(blk) * g;
             if (P2 <= 512) {                       // register-resident network (<= 16 elements per lane)
                 switch (P2) {
@@ -210,8 +211,8 @@ __global__ void __launch_bounds__(kThreadsOB, 4) window_order_blocks_kernel(cons
             // thread per (window, column)
             for (int it = threadIdx.x; it < nwin * P.n_features; it += kThreadsOB) {
                 const int wl = it / P.n_features, j = it - wl * P.n_features;
-                const InT* A = sorted + static_cast<size_t>(wl * P.hop) * P2;
-                const InT* B = P.k == 2 ? A + P2 : A;
+                const InT* A = sorted + static_cast<size_t>(wl * P.hop) * BS;
+                const InT* B = P.k == 2 ? A + BS : A;
                 const int gb = P.k == 2 ? g : 0;
                 const InT wmin = (gb && B[0] < A[0]) ? B[0] : A[0];
                 const InT wmax = (gb && B[g - 1] > A[g - 1]) ? B[g - 1] : A[g - 1];
@@ -255,7 +256,7 @@ __global__ void __launch_bounds__(kThreadsOB, 4) window_order_blocks_kernel(cons
             int len = 0;
             InT bmin = Key<InT>::inf(), bmax = -Key<InT>::inf();
             if (lb < P.k) {
-                const InT* blk = sorted + static_cast<size_t>(wl * P.hop + lb) * P2;
+                const InT* blk = sorted + static_cast<size_t>(wl * P.hop + lb) * BS;
                 const int start = sg * P.seglen;
                 len = g - start;
                 if (len > P.seglen) len = P.seglen;
@@ -319,14 +320,14 @@ int32_t window_order_blocks_try(const InT* x, const mhb_windows* geom, int64_t n
     if (k > 2 && k < 8) return -100;            // a few blocks per window: sorting the window is cheaper than bisecting
     if (k > 2) {
         // bisection costs one pass of <= 32 (64) probes per selected rank, the window sort is paid once whatever the
-        // number of columns: measured break-even (W = 1920, k = 30) between three and four ranks
+        // number of columns: measured (W = 1920, k = 30) 1.5 ms per rank against 18 ms for the sort
         int n_sel = 0;
         for (int j = 0; j < n_features; ++j) n_sel += h_features[j] == MHB_F_IQR ? 2 : 1;
-        if (n_sel > 3) return -100;
+        if (n_sel > 8) return -100;
     }
     int64_t p2 = 32;
     while (p2 < g) p2 <<= 1;
-    const int64_t block_bytes = p2 * static_cast<int64_t>(sizeof(InT));
+    const int64_t block_bytes = (p2 + 1) * static_cast<int64_t>(sizeof(InT));
     const int64_t nb_max = (32 * 1024) / block_bytes;
     if (nb_max < k) return -100;
     int64_t nwb = (nb_max - k) / hop + 1;
