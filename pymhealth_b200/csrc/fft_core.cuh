@@ -69,6 +69,13 @@ __device__ __forceinline__ void fill_twiddles(Cx<T>* tw, int n, int count, int r
     }
 }
 
+// Shared-memory index swizzle for the Stockham buffers: one slot of padding per 16 elements, so that the radix-R strided
+// stores of the early passes (stride R elements = a multiple of 16 for the big radices: every lane on the same bank)
+// spread over the banks.  PAD = 0 keeps the plain index (float64 transforms, exact-size buffers).
+template <int PAD>
+__device__ __forceinline__ int sidx(int i) { return PAD ? i + (i >> 4) : i; }
+static inline size_t padded_len(size_t n) { return n + (n >> 4) + 1; }
+
 // ---- register-resident butterflies (float32): primes 2 / 3 / 4 / 5 and Cooley-Tukey composites of them
 using Cf = Cx<float>;
 __device__ __forceinline__ void rdft2(Cf* a) {
@@ -169,7 +176,7 @@ template <>
 __device__ __forceinline__ void rdft<16>(Cf* a) { rdft_composite<16, 4, 4>(a); }
 
 // One Stockham pass of a composite radix (float32): same indexing as stockham_pass below
-template <int R>
+template <int R, int PAD>
 __device__ __forceinline__ void stockham_pass_composite(const Cf* __restrict__ in, Cf* __restrict__ out, int n, int ns,
                                                         const Cf* __restrict__ tw, int r, int G) {
     const int nb = n / R;
@@ -178,7 +185,7 @@ __device__ __forceinline__ void stockham_pass_composite(const Cf* __restrict__ i
         const int k = j % ns;
         Cf a[R];
 #pragma unroll
-        for (int t = 0; t < R; ++t) a[t] = in[j + t * nb];
+        for (int t = 0; t < R; ++t) a[t] = in[sidx<PAD>(j + t * nb)];
         if (ns > 1) {
 #pragma unroll
             for (int t = 1; t < R; ++t) a[t] = cmul(a[t], tw[t * k * tstep]);
@@ -186,13 +193,13 @@ __device__ __forceinline__ void stockham_pass_composite(const Cf* __restrict__ i
         rdft<R>(a);
         const int o = (j - k) * R + k;
 #pragma unroll
-        for (int t = 0; t < R; ++t) out[o + t * ns] = a[t];
+        for (int t = 0; t < R; ++t) out[sidx<PAD>(o + t * ns)] = a[t];
     }
 }
 
 // One Stockham pass of radix R: `in` -> `out`, both n complex values in shared memory.
 // ns = product of the radices already applied.  Executed by G threads with rank r.
-template <typename T, int R>
+template <typename T, int R, int PAD>
 __device__ __forceinline__ void stockham_pass(const Cx<T>* __restrict__ in, Cx<T>* __restrict__ out, int n, int ns,
                                               const Cx<T>* __restrict__ tw, int r, int G) {
     const int nb = n / R;                 // butterflies
@@ -201,7 +208,7 @@ __device__ __forceinline__ void stockham_pass(const Cx<T>* __restrict__ in, Cx<T
         const int k = j % ns;
         Cx<T> a[R];
 #pragma unroll
-        for (int t = 0; t < R; ++t) a[t] = in[j + t * nb];
+        for (int t = 0; t < R; ++t) a[t] = in[sidx<PAD>(j + t * nb)];
         if (ns > 1) {
 #pragma unroll
             for (int t = 1; t < R; ++t) a[t] = cmul(a[t], tw[t * k * tstep]);
@@ -242,12 +249,12 @@ __device__ __forceinline__ void stockham_pass(const Cx<T>* __restrict__ in, Cx<T
         }
         const int o = (j - k) * R + k;
 #pragma unroll
-        for (int t = 0; t < R; ++t) out[o + t * ns] = y[t];
+        for (int t = 0; t < R; ++t) out[sidx<PAD>(o + t * ns)] = y[t];
     }
 }
 
 // generic prime radix p (7..31): O(p^2) butterfly, DFT matrix entries from the twiddle table
-template <typename T>
+template <typename T, int PAD>
 __device__ __forceinline__ void stockham_pass_generic(const Cx<T>* __restrict__ in, Cx<T>* __restrict__ out, int n,
                                                       int ns, int p, const Cx<T>* __restrict__ tw, int r, int G) {
     const int nb = n / p;
@@ -257,19 +264,19 @@ __device__ __forceinline__ void stockham_pass_generic(const Cx<T>* __restrict__ 
         const int k = j % ns;
         const int o = (j - k) * p + k;
         for (int t = 0; t < p; ++t) {
-            Cx<T> acc = in[j];
+            Cx<T> acc = in[sidx<PAD>(j)];
             for (int u = 1; u < p; ++u) {
-                Cx<T> a = in[j + u * nb];
+                Cx<T> a = in[sidx<PAD>(j + u * nb)];
                 if (ns > 1) a = cmul(a, tw[u * k * tstep]);
                 acc = cadd(acc, cmul(a, tw[((t * u) % p) * pstep]));
             }
-            out[o + t * ns] = acc;
+            out[sidx<PAD>(o + t * ns)] = acc;
         }
     }
 }
 
 // Full transform.  Returns the buffer that holds the result (a or b).  sync() separates passes.
-template <typename T, typename SyncFn>
+template <typename T, int PAD = 0, typename SyncFn>
 __device__ __forceinline__ Cx<T>* stockham_fft(Cx<T>* a, Cx<T>* b, const FftPlan& plan, const Cx<T>* tw, int r, int G,
                                                SyncFn sync) {
     int ns = 1;
@@ -278,24 +285,24 @@ __device__ __forceinline__ Cx<T>* stockham_fft(Cx<T>* a, Cx<T>* b, const FftPlan
     for (int i = 0; i < plan.n_radices; ++i) {
         const int R = plan.radix[i];
         switch (R) {
-            case 2: stockham_pass<T, 2>(in, out, plan.n, ns, tw, r, G); break;
-            case 3: stockham_pass<T, 3>(in, out, plan.n, ns, tw, r, G); break;
-            case 4: stockham_pass<T, 4>(in, out, plan.n, ns, tw, r, G); break;
-            case 5: stockham_pass<T, 5>(in, out, plan.n, ns, tw, r, G); break;
+            case 2: stockham_pass<T, 2, PAD>(in, out, plan.n, ns, tw, r, G); break;
+            case 3: stockham_pass<T, 3, PAD>(in, out, plan.n, ns, tw, r, G); break;
+            case 4: stockham_pass<T, 4, PAD>(in, out, plan.n, ns, tw, r, G); break;
+            case 5: stockham_pass<T, 5, PAD>(in, out, plan.n, ns, tw, r, G); break;
             case 6:
             case 8:
             case 10:
             case 12:
             case 16:
                 if constexpr (sizeof(T) == 4) {            // composite radices exist for float32 plans only
-                    if (R == 6) stockham_pass_composite<6>(in, out, plan.n, ns, tw, r, G);
-                    else if (R == 8) stockham_pass_composite<8>(in, out, plan.n, ns, tw, r, G);
-                    else if (R == 10) stockham_pass_composite<10>(in, out, plan.n, ns, tw, r, G);
-                    else if (R == 12) stockham_pass_composite<12>(in, out, plan.n, ns, tw, r, G);
-                    else stockham_pass_composite<16>(in, out, plan.n, ns, tw, r, G);
+                    if (R == 6) stockham_pass_composite<6, PAD>(in, out, plan.n, ns, tw, r, G);
+                    else if (R == 8) stockham_pass_composite<8, PAD>(in, out, plan.n, ns, tw, r, G);
+                    else if (R == 10) stockham_pass_composite<10, PAD>(in, out, plan.n, ns, tw, r, G);
+                    else if (R == 12) stockham_pass_composite<12, PAD>(in, out, plan.n, ns, tw, r, G);
+                    else stockham_pass_composite<16, PAD>(in, out, plan.n, ns, tw, r, G);
                 }
                 break;
-            default: stockham_pass_generic<T>(in, out, plan.n, ns, R, tw, r, G); break;
+            default: stockham_pass_generic<T, PAD>(in, out, plan.n, ns, R, tw, r, G); break;
         }
         ns *= R;
         sync();

@@ -63,8 +63,10 @@ __global__ void __launch_bounds__(kWarps * 32) window_spectral_kernel(const Spec
     C* tw = reinterpret_cast<C*>(smem_raw);
     C* tw2 = tw + N;
     C* bufs = tw2 + (P.even ? P.nb : 0);
-    C* A = bufs + static_cast<size_t>(warp) * 2 * N;
-    C* B = A + N;
+    const int NP = N + (N >> 4) + 1;                 // padded buffer length (fft_core.cuh sidx<1>)
+    C* A = bufs + static_cast<size_t>(warp) * 2 * NP;
+    C* B = A + NP;
+    auto pd = [](int i) { return sidx<1>(i); };
 
     fill_twiddles<float>(tw, N, N, threadIdx.x, blockDim.x);
     if (P.even) fill_twiddles<float>(tw2, P.W, P.nb, threadIdx.x, blockDim.x);
@@ -86,14 +88,14 @@ __global__ void __launch_bounds__(kWarps * 32) window_spectral_kernel(const Spec
 #pragma unroll 4
                 for (int i = lane; i < N; i += 32) {
                     const float2 v = s2[i];
-                    A[i] = {v.x, v.y};
+                    A[pd(i)] = {v.x, v.y};
                     sum += static_cast<double>(v.x) + static_cast<double>(v.y);
                 }
             } else {
 #pragma unroll 4
                 for (int i = lane; i < N; i += 32) {
                     const float a0 = src[2 * i], a1 = src[2 * i + 1];
-                    A[i] = {a0, a1};
+                    A[pd(i)] = {a0, a1};
                     sum += static_cast<double>(a0) + static_cast<double>(a1);
                 }
             }
@@ -101,7 +103,7 @@ __global__ void __launch_bounds__(kWarps * 32) window_spectral_kernel(const Spec
 #pragma unroll 4
             for (int i = lane; i < N; i += 32) {
                 const float a0 = src[i];
-                A[i] = {a0, 0.f};
+                A[pd(i)] = {a0, 0.f};
                 sum += static_cast<double>(a0);
             }
         }
@@ -110,21 +112,21 @@ __global__ void __launch_bounds__(kWarps * 32) window_spectral_kernel(const Spec
         __syncwarp();
         if (P.even) {
 #pragma unroll 4
-            for (int i = lane; i < N; i += 32) A[i] = {A[i].x - mean, A[i].y - mean};
+            for (int i = lane; i < N; i += 32) A[pd(i)] = {A[pd(i)].x - mean, A[pd(i)].y - mean};
         } else {
 #pragma unroll 4
-            for (int i = lane; i < N; i += 32) A[i].x -= mean;
+            for (int i = lane; i < N; i += 32) A[pd(i)].x -= mean;
         }
         __syncwarp();
 
-        C* Z = stockham_fft<float>(A, B, P.fft, tw, lane, 32, [] { __syncwarp(); });
+        C* Z = stockham_fft<float, 1>(A, B, P.fft, tw, lane, 32, [] { __syncwarp(); });
         float* psd = reinterpret_cast<float*>(Z == A ? B : A);        // the free buffer, nb floats <= 2N floats
 
         // ---- one-sided power spectrum
         if (P.even) {
             for (int k = lane; k <= N; k += 32) {
-                const C zk = Z[k == N ? 0 : k];
-                const C zn = Z[k == 0 ? 0 : N - k];
+                const C zk = Z[pd(k == N ? 0 : k)];
+                const C zn = Z[pd(k == 0 ? 0 : N - k)];
                 const C e = {0.5f * (zk.x + zn.x), 0.5f * (zk.y - zn.y)};          // (Z[k] + conj Z[N-k]) / 2
                 const C o = {0.5f * (zk.y + zn.y), -0.5f * (zk.x - zn.x)};         // (Z[k] - conj Z[N-k]) / (2i)
                 const C t = cmul(o, tw2[k]);
@@ -132,7 +134,7 @@ __global__ void __launch_bounds__(kWarps * 32) window_spectral_kernel(const Spec
                 psd[k] = re * re + im * im;
             }
         } else {
-            for (int k = lane; k < P.nb; k += 32) psd[k] = Z[k].x * Z[k].x + Z[k].y * Z[k].y;
+            for (int k = lane; k < P.nb; k += 32) psd[k] = Z[pd(k)].x * Z[pd(k)].x + Z[pd(k)].y * Z[pd(k)].y;
         }
         __syncwarp();
         const double dc = sum * sum;              // bin 0 of the un-centred window, exact
@@ -291,7 +293,7 @@ int32_t spectral_launch(const float* x, const mhb_windows* geom, double fs, cons
     }
     // one warp per window, two N-point buffers per warp: pick the warps per CTA that pack the most warps on an SM
     const size_t shared_tab = sizeof(Cx<float>) * (static_cast<size_t>(P.N) + (P.even ? P.nb : 0));
-    const size_t per_warp = sizeof(Cx<float>) * 2 * static_cast<size_t>(P.N);
+    const size_t per_warp = sizeof(Cx<float>) * 2 * padded_len(static_cast<size_t>(P.N));
     MHB_REQUIRE(shared_tab + per_warp <= 200 * 1024, MHB_E_UNSUPPORTED, "%s: wsize=%d needs %zu bytes of shared memory", who,
                 P.W, shared_tab + per_warp);
     int best_warps = 1, best_total = 0;
