@@ -270,6 +270,25 @@ def run_b200_arm(args):
     total_ms, ms_stats, ms_spec = (float(v) for v in tmax.cpu())
     value = world * windows_per_step * args.steps / (total_ms * 1e-3)
 
+    # ---- outside the timed step: the order-statistics kernel (kernel 1b: median + 90th percentile) on a slice of the
+    # shard, reported next to the step's kernels (percentiles are part of the north-star feature list; the 16 bench
+    # columns, fixed in BASELINE.md's plan, hold none)
+    ms_order, order_series = None, min(24, nsub * 3)
+    if rank == 0:
+        from pymhealth_b200.generic import stats as _st
+        order_f = [_st.median.feature(), _st.percentile.feature(90.0)]
+        t_ord = torch.empty((order_series, nw, 2), dtype=torch.float32, device=dev)
+        engine.window_table(x[:order_series], WSIZE, WSTEP, order_f, out=t_ord)
+        o0, o1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        o0.record()
+        for _ in range(3):
+            engine.window_table(x[:order_series], WSIZE, WSTEP, order_f, out=t_ord)
+        o1.record()
+        torch.cuda.synchronize()
+        ms_order = o0.elapsed_time(o1) / 3
+        del t_ord
+
     # ---- end-to-end through the public host-buffer API (pinned host inputs, H2D + kernels + D2H per step)
     e2e_sub = min(args.e2e_subjects, nsub)
     numa_node = sharded.bind_host_to_device_numa(local)        # pinned buffers next to this GPU's PCIe root
@@ -341,7 +360,13 @@ def run_b200_arm(args):
                        "l2": "inputs (%.1f GB per GPU) are far larger than the 126 MB L2; no flush needed" % (samples_b / 1e9),
                        "parallelism": "subject-sharded x%d, no data-path collective" % world},
             "roofline": dominant,
-            "kernels": {"window_stats": k_stats, "window_spectral": k_spec},
+            "kernels": {"window_stats": k_stats, "window_spectral": k_spec,
+                        "window_order (not in the step)": {
+                            "kernel": "window_order_blocks_kernel (kernel 1b: median + p90)", "bound": "sm (sorting)",
+                            "series": order_series, "ms_per_launch": ms_order,
+                            "windows_per_s": order_series * nw / (ms_order * 1e-3) if ms_order else None,
+                            "achieved": (order_series * n * 4 + order_series * nw * 8) / (ms_order * 1e-3) / 1e9 if ms_order else None,
+                            "unit": "GB/s"}},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(hx.numel() * 4),
                     "d2h_bytes_per_step": int(hout.numel() * 4), "subjects_per_step_per_gpu": e2e_sub,
                     "ms_per_step": float(e2e_ms.cpu()) / e2e_steps, "matches_resident_run": check_ok,
