@@ -188,12 +188,14 @@ int32_t mhb_accel_magnitude_dot(int32_t is_f64, const void* x, const void* y, co
                                 double* workspace, int64_t workspace_len, double* out, void* stream);
 
 /* ---- successive-difference statistics (HRV time-domain metrics, src/mhealth/heart/hrv.py:111-170) ---------
- * out6 = {n - 1, sum(diff), mean(diff), var(diff) (population), count(|diff| > abs_threshold), mean(diff^2)}:
- * pnnx = out[4] / out[0], rmssd = sqrt(out[5]), ssd = out[1], sdsd = sqrt(out[3]).
+ * out7 = {n - 1, sum(diff), mean(diff), var(diff) (population), count(|diff| > abs_threshold), mean(diff^2),
+ *         var(x[i+1] + x[i]) (population)}:
+ * pnnx = out[4] / out[0], rmssd = sqrt(out[5]), ssd = out[1], sdsd = sqrt(out[3]); the Poincare widths
+ * csi_sd1 = factor * sqrt(out[3]), csi_sd2 = factor * sqrt(out[6]) (hrv.py:207-231).
  * workspace: mhb_diff_stats_workspace(n - 1) doubles. */
 int64_t mhb_diff_stats_workspace(int64_t n_diff);
 int32_t mhb_diff_stats_f64(const double* x, int64_t n, double abs_threshold, double* workspace, int64_t workspace_len,
-                           double* out6, void* stream);
+                           double* out7, void* stream);
 
 /* timedom.gradient(x) (src/mhealth/generic/timedom.py:11-31) -> float64 [n] (differences in the input type);
  * timedom.zero_crossings(x, th) (:34-49) -> n - 1 flags, one byte each. */

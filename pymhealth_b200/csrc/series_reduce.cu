@@ -10,34 +10,43 @@ namespace mhb {
 namespace {
 
 struct DiffRec {
-    double s1, s2;
+    double s1, s2;      // shifted power sums of the differences x[i+1] - x[i]
+    double t1, t2;      // ... and of the pair sums x[i+1] + x[i] (Poincare SD2, hrv.py:219-231)
     long long cnt;
 };
 
 __global__ void __launch_bounds__(256) diff_partial_kernel(const double* __restrict__ x, int64_t nd, double thr,
                                                            DiffRec* __restrict__ part) {
     __shared__ DiffRec sh[8];
-    const double c = x[1] - x[0];
-    double s1 = 0.0, s2 = 0.0;
+    const double c = x[1] - x[0], c2 = x[1] + x[0];
+    double s1 = 0.0, s2 = 0.0, t1 = 0.0, t2 = 0.0;
     long long cnt = 0;
     const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
     for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < nd; i += stride) {
-        const double d = x[i + 1] - x[i];
+        const double a = x[i], b = x[i + 1];
+        const double d = b - a;
         const double e = d - c;
         s1 += e;
         s2 = fma(e, e, s2);
+        const double f = (b + a) - c2;
+        t1 += f;
+        t2 = fma(f, f, t2);
         cnt += fabs(d) > thr ? 1 : 0;
     }
     s1 = warp_sum(s1);
     s2 = warp_sum(s2);
+    t1 = warp_sum(t1);
+    t2 = warp_sum(t2);
     cnt = warp_sum(cnt);
-    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = {s1, s2, cnt};
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = {s1, s2, t1, t2, cnt};
     __syncthreads();
     if (threadIdx.x == 0) {
-        DiffRec t = {0.0, 0.0, 0};
+        DiffRec t = {0.0, 0.0, 0.0, 0.0, 0};
         for (int i = 0; i < 8; ++i) {
             t.s1 += sh[i].s1;
             t.s2 += sh[i].s2;
+            t.t1 += sh[i].t1;
+            t.t2 += sh[i].t2;
             t.cnt += sh[i].cnt;
         }
         part[blockIdx.x] = t;
@@ -47,10 +56,12 @@ __global__ void __launch_bounds__(256) diff_partial_kernel(const double* __restr
 __global__ void diff_final_kernel(const double* __restrict__ x, int64_t nd, const DiffRec* __restrict__ part, int n_part,
                                   double* __restrict__ out) {
     if (threadIdx.x != 0) return;
-    DiffRec t = {0.0, 0.0, 0};
+    DiffRec t = {0.0, 0.0, 0.0, 0.0, 0};
     for (int i = 0; i < n_part; ++i) {
         t.s1 += part[i].s1;
         t.s2 += part[i].s2;
+        t.t1 += part[i].t1;
+        t.t2 += part[i].t2;
         t.cnt += part[i].cnt;
     }
     const double c = x[1] - x[0];
@@ -65,6 +76,9 @@ __global__ void diff_final_kernel(const double* __restrict__ x, int64_t nd, cons
     out[3] = m2 / n;                   // population variance of diff
     out[4] = static_cast<double>(t.cnt);
     out[5] = m2 / n + mean * mean;     // mean(diff^2)
+    double p2 = t.t2 - t.t1 * (t.t1 / n);
+    if (p2 < 0.0) p2 = 0.0;
+    out[6] = p2 / n;                   // population variance of the pair sums x[i+1] + x[i]
 }
 
 // ppg.slope_sum (src/mhealth/heart/ppg.py:28-42): out[i] = sum(dx[i-w : i]) for w <= i < n - 1, 0 elsewhere,
@@ -169,21 +183,21 @@ extern "C" int64_t mhb_diff_stats_workspace(int64_t n) {
     const int64_t cap = static_cast<int64_t>(mhb::kNumSMs) * 4;
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
-    return blocks * 3;                 // doubles (one 24-byte record per CTA)
+    return blocks * 5;                 // doubles (one 40-byte record per CTA)
 }
 
 extern "C" int32_t mhb_diff_stats_f64(const double* x, int64_t n, double abs_threshold, double* workspace,
-                                      int64_t workspace_len, double* out6, void* stream) {
+                                      int64_t workspace_len, double* out7, void* stream) {
     using namespace mhb;
     MHB_REQUIRE(n >= 2, MHB_E_ARG, "diff_stats: at least two samples are needed (n = %lld)", static_cast<long long>(n));
-    MHB_REQUIRE(x && workspace && out6, MHB_E_ARG, "diff_stats: null pointer");
+    MHB_REQUIRE(x && workspace && out7, MHB_E_ARG, "diff_stats: null pointer");
     const int64_t need = mhb_diff_stats_workspace(n - 1);
     MHB_REQUIRE(workspace_len >= need, MHB_E_WORKSPACE, "diff_stats: workspace of %lld doubles needed",
                 static_cast<long long>(need));
-    const int blocks = static_cast<int>(need / 3);
+    const int blocks = static_cast<int>(need / 5);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     DiffRec* part = reinterpret_cast<DiffRec*>(workspace);
     diff_partial_kernel<<<blocks, 256, 0, s>>>(x, n - 1, abs_threshold, part);
-    diff_final_kernel<<<1, 32, 0, s>>>(x, n - 1, part, blocks, out6);
+    diff_final_kernel<<<1, 32, 0, s>>>(x, n - 1, part, blocks, out7);
     return cuda_status(cudaGetLastError(), "diff_stats launch");
 }

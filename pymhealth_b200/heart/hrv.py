@@ -57,7 +57,7 @@ def _diff_stats(nni, threshold=0.0):
     d = torch.from_numpy(a).cuda()
     wlen = int(lib.mhb_diff_stats_workspace(a.shape[0] - 1))
     ws = torch.empty(wlen, dtype=torch.float64, device=d.device)
-    out = torch.empty(6, dtype=torch.float64, device=d.device)
+    out = torch.empty(7, dtype=torch.float64, device=d.device)
     L.check(lib.mhb_diff_stats_f64(d.data_ptr(), a.shape[0], float(threshold), ws.data_ptr(), wlen, out.data_ptr(),
                                    _stream_ptr(torch)), "diff_stats")
     return out.cpu().numpy()
@@ -127,3 +127,37 @@ def sdnni(nni, index=None, interval: float = 60 * 5, unit=None) -> float:
     step = int(interval * 1e9)
     sds = nonuniform_rolling_apply(np.std)(idx, np.asarray(nni, dtype=np.float64), step, step)
     return float(stats.mean(sds))
+
+
+# Non-linear (Poincare / Lorenz plot) indices, hrv.py:207-266
+def csi_sd1(rri, factor: float = 1 / np.sqrt(2)) -> float:
+    """Poincare plot width: factor * std(diff(rri)) (hrv.py:207-216)."""
+    return float(factor * np.sqrt(_diff_stats(rri)[3]))
+
+
+def csi_sd2(rri, factor: float = 1 / np.sqrt(2)) -> float:
+    """Poincare plot length: factor * std(rri[1:] + rri[:-1]) (hrv.py:219-231)."""
+    return float(factor * np.sqrt(_diff_stats(rri)[6]))
+
+
+def _sd12(rri, factor):
+    r = _diff_stats(rri)
+    return factor * np.sqrt(r[3]), factor * np.sqrt(r[6])
+
+
+def lorenz_csi(rri, factor: float = 1 / np.sqrt(2)) -> float:
+    """Cardiac sympathetic index sd1 / sd2 (hrv.py:234-243)."""
+    a, b = _sd12(rri, factor)
+    return float(a / b)
+
+
+def lorenz_cvi(rri, factor: float = 1 / np.sqrt(2)) -> float:
+    """log10(sd1 * sd2) (hrv.py:246-250)."""
+    a, b = _sd12(rri, factor)
+    return float(np.log10(a * b))
+
+
+def lorenz_mcsi(rri, factor: float = 1 / np.sqrt(2)) -> float:
+    """Modified sympathetic index sd1^2 / sd2 (hrv.py:253-266)."""
+    a, b = _sd12(rri, factor)
+    return float(a ** 2 / b)

@@ -243,6 +243,8 @@ def extra_fixture():
     out["hrv/ssd"] = np.array(hrv.ssd(rr))
     out["hrv/sdsd"] = np.array(hrv.sdsd(rr))
     out["hrv/nni_to_ms"] = hrv.nni_to_ms(rr[:16] * 1e6, 'ns')
+    out["hrv/poincare"] = np.array([hrv.csi_sd1(rr), hrv.csi_sd2(rr), hrv.lorenz_csi(rr), hrv.lorenz_cvi(rr),
+                                    hrv.lorenz_mcsi(rr), hrv.csi_sd2(rr, 0.5)])
     g = a64[2][:2001].copy()
     out["td/x"] = g
     out["td/gradient_f64"] = timedom.gradient(g)

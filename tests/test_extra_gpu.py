@@ -78,6 +78,8 @@ def test_hrv_time_domain_golden(ref_extra):
     assert hrv.ssd(rr) == pytest.approx(float(ref_extra["hrv/ssd"]), rel=1e-9, abs=1e-9)
     assert hrv.sdsd(rr) == pytest.approx(float(ref_extra["hrv/sdsd"]), rel=1e-12)
     np.testing.assert_array_equal(hrv.nni_to_ms(rr[:16] * 1e6, 'ns'), ref_extra["hrv/nni_to_ms"])
+    got = [hrv.csi_sd1(rr), hrv.csi_sd2(rr), hrv.lorenz_csi(rr), hrv.lorenz_cvi(rr), hrv.lorenz_mcsi(rr), hrv.csi_sd2(rr, 0.5)]
+    np.testing.assert_allclose(got, ref_extra["hrv/poincare"], rtol=1e-11)                 # Poincare / Lorenz indices
     with pytest.raises(ValueError):
         hrv.td_factor("h")
     # segment metrics: the reference's own versions do not compile under numba 0.65 (parity unpinned) -> oracle
