@@ -43,7 +43,7 @@ constexpr int kThreadsF = 256;           // 16 half-warps: 10 pass-A roles / 13 
 constexpr int kNA = 10;                  // pass-A threads per window (n2)
 constexpr int kNP = 13;                  // pass-B threads per window (p = 0..12)
 constexpr int kWSB = 251;                // complex stride between windows in buf (odd: conflict free)
-constexpr int kRowStride = 253;          // float stride between PSD rows (odd: conflict free)
+constexpr int kRowStride = 254;          // float stride between PSD rows: 2 x odd, so the 16 windows of the two roles of a warp (bins k and k + 1) cover all 32 banks
 constexpr int kMaxColsF = 32;
 constexpr int kTileElems = ((kBW - 1) * kS + kW + 3 + 4) & ~3;     // 4256 floats
 static_assert(2 * kBW + kBW * kRowStride <= kTileElems, "PSD rows + DC cells must fit a consumed tile slot");
