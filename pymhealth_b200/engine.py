@@ -55,12 +55,19 @@ def to_device_series(x):
     if was_numpy:
         a = np.asarray(x)
         if a.dtype == np.float32 or a.dtype == np.float64:
-            pass
-        elif a.dtype.kind in "iub" or a.dtype == np.float16:
-            a = a.astype(np.float64)          # exact for <= 32-bit integers
+            t = torch.from_numpy(np.ascontiguousarray(a)).cuda(non_blocking=False)
+        elif a.dtype in (np.int8, np.uint8, np.int16, np.uint16, np.float16, np.bool_):
+            # raw sensor counts: upload as they are (2 bytes per sample over PCIe) and widen on the device; every value
+            # is exact in float32, and the kernels accumulate in float64 either way
+            raw = a.view(np.uint8) if a.dtype == np.bool_ else a
+            if raw.dtype == np.uint16:
+                raw = raw.astype(np.int32)                 # torch has no uint16 arithmetic
+            t = torch.from_numpy(np.ascontiguousarray(raw)).cuda(non_blocking=False).float()
+        elif a.dtype.kind in "iu":
+            raw = a.astype(np.int64) if a.dtype in (np.uint32, np.uint64) else a
+            t = torch.from_numpy(np.ascontiguousarray(raw)).cuda(non_blocking=False).double()   # exact for 32-bit integers
         else:
             raise TypeError("unsupported dtype %s" % a.dtype)
-        t = torch.from_numpy(np.ascontiguousarray(a)).cuda(non_blocking=False)
     else:
         t = x
         if not t.is_cuda:

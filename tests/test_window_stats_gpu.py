@@ -148,3 +148,22 @@ def test_size_independent_properties_full_config2():
     # (4) shift invariance of the window grid: dropping the first hop shifts the table by one row
     tab3 = engine.window_table(x[:, 250:], 500, 250, feats, out_dtype=torch.float64)
     torch.testing.assert_close(tab3[:, :, :4], tab[:, 1:, :4], rtol=1e-10, atol=1e-12)
+
+
+def test_integer_sensor_counts():
+    """int16 / uint8 / int32 input (raw counts): widened on the device, same results as the float64 oracle."""
+    from oracle import windows as OW
+    from pymhealth_b200.util import rolling_apply
+    from pymhealth_b200.generic import stats, timedom
+    rng = np.random.default_rng(3)
+    for dt, lo, hi in ((np.int16, -2000, 2000), (np.uint8, 0, 255), (np.int32, -10**6, 10**6)):
+        x = rng.integers(lo, hi, 7000).astype(dt)
+        got = rolling_apply([np.mean, np.var, np.min, np.max, stats.skewness, np.median,
+                             functools.partial(timedom.zero_crossing_count, th=0.0)])(x, 128, 32)
+        for g, name in zip(got, ["mean", "var", "min", "max", "skewness", "median", "zero_crossing_count"]):
+            want = OW.rolling(name, x.astype(np.float64), 128, 32, 0.0)
+            assert g.dtype == np.float64
+            if name in ("min", "max", "median", "zero_crossing_count"):
+                np.testing.assert_array_equal(g, want, err_msg="%s %s" % (dt.__name__, name))
+            else:
+                np.testing.assert_allclose(g, want, rtol=1e-9, atol=1e-9, err_msg="%s %s" % (dt.__name__, name))
