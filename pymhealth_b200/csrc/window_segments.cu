@@ -35,6 +35,9 @@ struct SegPlan {
     int64_t o_window, o_col;
     int32_t n_features;
     int32_t feat[kMaxFeatSeg];
+    // uniform mode (starts == nullptr): window w of nw per series starts at series * series_stride + wi * S, length W
+    int64_t nw, series_stride, o_series;
+    int32_t W, S;
 };
 
 struct SegAcc {
@@ -141,11 +144,22 @@ __device__ __forceinline__ void seg_emit(const SegPlan& P, int64_t w, int64_t le
                 default: break;
             }
         }
-        store_cell<OutT>(P.out, w * P.o_window + j * P.o_col, v);
+        int64_t row = w * P.o_window;
+        if (P.starts == nullptr) {
+            const int64_t series = w / P.nw;
+            row = series * P.o_series + (w - series * P.nw) * P.o_window;
+        }
+        store_cell<OutT>(P.out, row + j * P.o_col, v);
     }
 }
 
 __device__ __forceinline__ void seg_bounds(const SegPlan& P, int64_t w, int64_t& s, int64_t& e) {
+    if (P.starts == nullptr) {
+        const int64_t series = w / P.nw, wi = w - series * P.nw;
+        s = series * P.series_stride + wi * P.S;
+        e = s + P.W;
+        return;
+    }
     s = P.starts[w];
     e = P.ends[w];
     // arr[si:ei] slicing clamps to the array (negative, i.e. from-the-end, indices are not produced by get_indices)
@@ -221,6 +235,49 @@ int32_t segment_stats_impl(const InT* x, int64_t n, const int64_t* starts, const
         segment_stats_kernel<InT, double><<<static_cast<unsigned>(ctas), kSegThreads, 0, stream>>>(P);
     return cuda_status(cudaGetLastError(), "segment_stats launch");
 }
+
+}  // namespace
+
+// Uniform windows through the warp-per-window kernel: the fallback of mhb_window_stats_* for geometries whose block
+// decomposition degenerates (gcd(W, S) so small that a window is more than ~1000 blocks, e.g. co-prime W and S).
+// Every window is evaluated directly from global memory (overlapping windows re-read L2), which is what the
+// reference's loop does too; all other geometries take the streaming kernel.
+template <typename InT>
+int32_t window_stats_direct(const InT* x, const mhb_windows* geom, int64_t nw, const int32_t* h_features,
+                            int32_t n_features, double zc_threshold, const mhb_table* table, void* stream_v) {
+    SegPlan P;
+    memset(&P, 0, sizeof(P));
+    for (int j = 0; j < n_features; ++j) P.feat[j] = h_features[j];
+    P.x = x;
+    P.n = (geom->n_series - 1) * geom->series_stride + geom->series_len;
+    P.n_windows = nw * geom->n_series;
+    P.min_len = 1;
+    P.th = zc_threshold > 0.0 ? zc_threshold : 0.0;
+    P.out = table->out;
+    P.o_window = table->window_stride;
+    P.o_col = table->column_stride;
+    P.o_series = table->series_stride;
+    P.n_features = n_features;
+    P.nw = nw;
+    P.series_stride = geom->series_stride;
+    P.W = geom->wsize;
+    P.S = geom->wstep;
+    int64_t ctas = (P.n_windows + 7) / 8;
+    const int64_t cap = static_cast<int64_t>(kNumSMs) * 8;
+    if (ctas > cap) ctas = cap;
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+    if (table->out_f32)
+        segment_stats_kernel<InT, float><<<static_cast<unsigned>(ctas), kSegThreads, 0, stream>>>(P);
+    else
+        segment_stats_kernel<InT, double><<<static_cast<unsigned>(ctas), kSegThreads, 0, stream>>>(P);
+    return cuda_status(cudaGetLastError(), "window_stats (direct) launch");
+}
+template int32_t window_stats_direct<float>(const float*, const mhb_windows*, int64_t, const int32_t*, int32_t, double,
+                                            const mhb_table*, void*);
+template int32_t window_stats_direct<double>(const double*, const mhb_windows*, int64_t, const int32_t*, int32_t, double,
+                                             const mhb_table*, void*);
+
+namespace {
 
 // ---- get_indices: left searchsorted of first + i*step (starts) and first + i*step + size (ends)
 template <typename T>

@@ -27,6 +27,11 @@
 
 namespace mhb {
 
+// window_segments.cu: warp-per-window evaluation of uniform windows (fallback for degenerate block decompositions)
+template <typename InT>
+int32_t window_stats_direct(const InT* x, const mhb_windows* geom, int64_t nw, const int32_t* h_features,
+                            int32_t n_features, double zc_threshold, const mhb_table* table, void* stream_v);
+
 namespace {
 
 constexpr int kThreads = 256;
@@ -695,9 +700,8 @@ int32_t window_stats_impl(const InT* x, const mhb_windows* geom, const int32_t* 
     }
     P.g = static_cast<int32_t>(g);
     const int64_t k64 = P.W / g, hop64 = P.S / g;
-    MHB_REQUIRE(k64 + hop64 <= 1024, MHB_E_UNSUPPORTED,
-                "window_stats: wsize=%d wstep=%d needs %lld + %lld blocks per window/hop (> 1024)", P.W, P.S,
-                (long long)k64, (long long)hop64);
+    if (k64 + hop64 > 1024)        // e.g. co-prime W and S: no block sharing to exploit, evaluate every window directly
+        return window_stats_direct<InT>(x, geom, nw, h_features, n_features, zc_threshold, table, stream_v);
     P.k = static_cast<int32_t>(k64);
     P.hop = static_cast<int32_t>(hop64);
     const CellChoice cc = choose_cell(g, sizeof(InT) == 4 && geom->series_stride % 4 == 0);
@@ -730,7 +734,8 @@ int32_t window_stats_impl(const InT* x, const mhb_windows* geom, const int32_t* 
     smem += partial_bytes(sizeof(InT), m4, td, P.RB);
     if (P.k > kDirectK) smem += sizeof(double) * kNPre * (P.RB + 1);
     smem += 64;
-    MHB_REQUIRE(smem <= 220 * 1024, MHB_E_UNSUPPORTED, "window_stats: geometry needs %zu bytes of shared memory", smem);
+    if (smem > 220 * 1024)           // ring + prefix arrays of an awkward (k, hop) do not fit: evaluate every window directly
+        return window_stats_direct<InT>(x, geom, nw, h_features, n_features, zc_threshold, table, stream_v);
 
     // chunking: enough CTAs to fill the machine several times, each long enough to amortise the
     // pipeline fill and the (k - hop) halo blocks, short enough to keep the pivot local

@@ -66,7 +66,9 @@ def test_golden_streaming(ref_windows, case):
 
 @pytest.mark.parametrize("n,W,S", [(4321, 500, 250), (10000, 1920, 64), (999, 64, 48), (257, 7, 3),
                                    (5000, 100, 100), (3000, 90, 120), (2048, 256, 32), (1500, 33, 1),
-                                   (700, 700, 5), (40000, 500, 250), (100, 101, 1), (100, 100, 1)])
+                                   (700, 700, 5), (40000, 500, 250), (100, 101, 1), (100, 100, 1),
+                                   # co-prime / awkward geometries: no block sharing -> the direct (warp per window) fallback
+                                   (30000, 479, 713), (9000, 1021, 7), (20000, 997, 2), (50000, 613, 411)])
 def test_oracle_random_geometries(n, W, S):
     from oracle import windows as OW
     from pymhealth_b200.util import rolling_apply
