@@ -20,7 +20,7 @@ def main():
     rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 0)
     bad = 0
     for case in range(ncases):
-        kind = case % 4
+        kind = case % 7
         if kind == 0:          # order statistics: geometries that hit the block paths (k <= 2, k >= 8) and the full sort
             g = int(rng.choice([16, 24, 32, 50, 64, 100, 125, 250, 256, 300]))
             k = int(rng.choice([1, 2, 2, 2, 3, 5, 8, 12, 30]))
@@ -78,6 +78,73 @@ def main():
             if not ok:
                 bad += 1
                 print("SPECTRAL MISMATCH W=%d S=%d n=%d fs=%g" % (W, S, n, fs))
+        elif kind == 4:        # location: random segment boundaries (empty ones included), random thresholds
+            from oracle import location_ext as OX
+            from pymhealth_b200 import synth, _lib as L
+            from pymhealth_b200.location import features
+            n = int(rng.integers(200, 6000))
+            lat, lon, t, home = synth.gps(int(rng.integers(0, 10**6)), n, int(rng.choice([1, 10, 60])))
+            cuts = np.sort(rng.integers(0, n + 1, int(rng.integers(0, 8))))
+            offs = np.concatenate([[0], cuts, [n]]).astype(np.int64)
+            homes = np.tile(np.array(home), (len(offs) - 1, 1)) + rng.normal(0, 1e-3, (len(offs) - 1, 2))
+            limit, sd, mins = float(rng.choice([0.05, 0.1, 1.0])), float(rng.choice([0.05, 0.2, 0.5])), int(rng.choice([60, 600, 1800]))
+            rows, labels = features.segment_rows(lat, lon, t, offs, homes, limit, sd, mins, labels=True)
+            want, wlab = OX.segment_features(lat, lon, t, offs, homes, limit, sd, mins)
+            ok = np.array_equal(labels, wlab)
+            for c, name in enumerate(L.SEG_COLUMNS):
+                if name in ("n_points", "home_stay_count", "n_stay_points", "n_labels"):
+                    ok = ok and np.array_equal(rows[:, c], want[:, c])
+                else:
+                    ok = ok and np.allclose(rows[:, c], want[:, c], rtol=1e-9, atol=1e-12, equal_nan=True)
+            if not ok:
+                bad += 1
+                print("LOCATION MISMATCH n=%d segments=%d limit=%g sd=%g mins=%d" % (n, len(offs) - 1, limit, sd, mins))
+        elif kind == 5:        # float64 multi-series device tensors through the engine
+            import torch
+            from pymhealth_b200 import engine
+            ns, W, S = int(rng.integers(1, 5)), int(rng.integers(2, 300)), int(rng.integers(1, 300))
+            n = W + S * int(rng.integers(0, 40)) + int(rng.integers(0, S))
+            x = rng.standard_normal((ns, n)) * 3 + 10
+            feats = [stats.mean.feature(), stats.std.feature(), stats.dmax.feature(), stats.median.feature(),
+                     timedom.hjorth_mobility.feature(), stats.mode.feature()]
+            x[:, ::3] = np.round(x[:, ::3])          # ties for the mode
+            if W < 2:
+                continue
+            tab = engine.window_table(torch.from_numpy(x).cuda(), W, S, feats, out_dtype=torch.float64).cpu().numpy()
+            for si in range(ns):
+                for c, nm in enumerate(["mean", "std", "max", "median", "hjorth_mobility", "mode"]):
+                    want = OW.rolling(nm, x[si], W, S)
+                    if not np.allclose(tab[si, :, c], want, rtol=1e-9, atol=1e-12, equal_nan=True):
+                        bad += 1
+                        print("F64 MISMATCH ns=%d W=%d S=%d n=%d %s" % (ns, W, S, n, nm))
+        elif kind == 6:        # spectral fast path, many columns with random (possibly empty / full) ranges
+            fs = 50.0
+            n = 500 + 250 * int(rng.integers(0, 70)) + int(rng.integers(0, 250))
+            tt = np.arange(n) / fs
+            x = (rng.choice([0.0, 1.0, -2.0]) + 0.4 * np.sin(2 * np.pi * rng.uniform(0.3, 20) * tt) + rng.choice([0.0, 0.05]) *
+                 rng.standard_normal(n)).astype(np.float32)
+            bands = [(float(a), float(a + b)) for a, b in zip(rng.uniform(0, 20, 5), rng.uniform(0.05, 10, 5))]
+            plo, phi = float(rng.uniform(0, 5)), float(rng.uniform(6, 25))
+            funcs = [SP.total_power(fs)] + [SP.band_power(fs, lo_, hi_) for lo_, hi_ in bands] + \
+                    [SP.relative_band_power(fs, *bands[0]), SP.peak_bin(fs, plo, phi), SP.peak_bin(fs), SP.spectral_entropy(fs)]
+            got = rolling_apply(funcs)(x, 500, 250)
+            tab = OS.spectral_table(x, 500, 250, fs, bands, plo, phi)
+            tot = tab["total_power"]
+            ok = np.all(np.abs(got[0] - tot) <= 1e-5 * np.maximum(tot, 1e-30))
+            for j in range(5):
+                ok = ok and np.all(np.abs(got[1 + j] - tab["band_power_%d" % j]) <= 1e-5 * np.maximum(tab["band_power_%d" % j], 1e-3 * tot) + 1e-30)
+            psd_ref, freqs = OS.window_psd(x, 500, 250, fs)
+            lidx, uidx = OS.first_index(freqs, plo), OS.first_index(freqs, phi)
+            pb = got[7].astype(np.int64)
+            wantb = lidx + np.argmax(psd_ref[:, lidx:uidx], axis=1)
+            for i in np.nonzero(pb != wantb)[0]:
+                a_, b_ = psd_ref[i, pb[i]], psd_ref[i, wantb[i]]
+                ok = ok and abs(a_ - b_) <= 1e-5 * max(b_, 1e-3 * tot[i])
+            if np.all(tot > 0):
+                ok = ok and np.allclose(got[9], tab["spectral_entropy"], rtol=1e-5, atol=1e-9)
+            if not ok:
+                bad += 1
+                print("SPECTRAL-FAST MISMATCH n=%d bands=%s peak=(%g,%g)" % (n, bands, plo, phi))
         else:                  # non-uniform windows
             n = int(rng.integers(50, 5000))
             idx = np.cumsum(rng.integers(1, 5, n)).astype(np.int64)
