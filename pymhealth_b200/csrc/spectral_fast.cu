@@ -30,6 +30,7 @@
 
 #include "fft_consts.cuh"
 #include "fft_core.cuh"
+#include "psd_entropy.cuh"
 
 namespace mhb {
 
@@ -236,7 +237,22 @@ __device__ __forceinline__ void reduce_rows(const FastPlan& P, const float* __re
             const float inv_t = __fdividef(1.0f, tf);
             const float p0 = static_cast<float>(dc) * inv_t, qrest = static_cast<float>(rest) * inv_t;
             const float h0 = p0 > 0.f ? -p0 * (qrest < 0.5f ? log1pf(-qrest) : __logf(p0)) : 0.f;   // log1p near p0 = 1
-            v = total > 0.0 ? static_cast<double>(fmaf(0.69314718055994530942f, hrest2, h0)) : CUDART_NAN;
+            const float hf = fmaf(0.69314718055994530942f, hrest2, h0);
+            v = total > 0.0 ? static_cast<double>(hf) : CUDART_NAN;
+            if (total > 0.0 && hf < kToneEntropy && p0 < 0.5f) {      // noiseless tone: psd_entropy.cuh (both lanes of
+                const unsigned pm = 3u << (lane & 30);                // the pair hold the same bits and branch together)
+                v = entropy_dominant_bin(
+                    prow, kN + 1, dc, total, j, 2,
+                    [pm](float& b, int& a) {
+                        const float ob = __shfl_xor_sync(pm, b, 1);
+                        const int oa = __shfl_xor_sync(pm, a, 1);
+                        if (ob > b || (ob == b && oa < a)) {
+                            b = ob;
+                            a = oa;
+                        }
+                    },
+                    [pm](double s) { return s + __shfl_xor_sync(pm, s, 1); });
+            }
         } else if (kind == MHB_S_BAND_POWER || kind == MHB_S_REL_BAND_POWER) {
             float a0 = 0.f, a1 = 0.f;
             int k = (lo > 1 ? lo : 1) + j;

@@ -21,6 +21,7 @@
 #include <math_constants.h>
 
 #include "fft_core.cuh"
+#include "psd_entropy.cuh"
 
 namespace mhb {
 
@@ -366,6 +367,7 @@ __global__ void __launch_bounds__(kT, 3) spectral_w1920_kernel(const Plan1920 P)
             for (int c = 0; c < P.n_cols; ++c) {
                 const int kind = P.col[c], ref = P.cref[c];
                 double v;
+                bool redo = false;
                 if (kind == MHB_S_TOTAL_POWER) {
                     v = total;
                 } else if (kind == MHB_S_ENTROPY) {
@@ -393,7 +395,9 @@ __global__ void __launch_bounds__(kT, 3) spectral_w1920_kernel(const Plan1920 P)
                     const float inv_t = __fdividef(1.0f, tf);
                     const float pz = static_cast<float>(dc) * inv_t, qrest = static_cast<float>(rest) * inv_t;
                     const float h0 = pz > 0.f ? -pz * (qrest < 0.5f ? log1pf(-qrest) : __logf(pz)) : 0.f;
-                    v = total > 0.0 ? static_cast<double>(fmaf(0.69314718055994530942f, hrest2, h0)) : CUDART_NAN;
+                    const float hf = fmaf(0.69314718055994530942f, hrest2, h0);
+                    v = total > 0.0 ? static_cast<double>(hf) : CUDART_NAN;
+                    redo = total > 0.0 && hf < kToneEntropy && pz < 0.5f;        // noiseless tone: psd_entropy.cuh
                 } else if (kind == MHB_S_BAND_POWER || kind == MHB_S_REL_BAND_POWER) {
                     const float* ps = psum + ref * kBW * kNP + q0;
                     float acc = ps[lane] + (two ? ps[lane + 32] : 0.f);
@@ -434,8 +438,14 @@ __global__ void __launch_bounds__(kT, 3) spectral_w1920_kernel(const Plan1920 P)
                 }
                 if (lane == 0) {
                     const int64_t o = static_cast<int64_t>(series) * P.o_series + (w0 + w) * P.o_window + c * P.o_col;
-                    if (P.out_f32) reinterpret_cast<float*>(P.out)[o] = static_cast<float>(v);
-                    else reinterpret_cast<double*>(P.out)[o] = v;
+                    if (redo) {
+                        if (P.out_f32) reinterpret_cast<uint32_t*>(P.out)[o] = kRedoMarkF32;
+                        else reinterpret_cast<unsigned long long*>(P.out)[o] = kRedoMarkF64;
+                    } else if (P.out_f32) {
+                        reinterpret_cast<float*>(P.out)[o] = static_cast<float>(v);
+                    } else {
+                        reinterpret_cast<double*>(P.out)[o] = v;
+                    }
                 }
             }
         }

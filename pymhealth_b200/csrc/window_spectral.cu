@@ -21,6 +21,7 @@
 #include <math_constants.h>
 
 #include "fft_core.cuh"
+#include "psd_entropy.cuh"
 
 namespace mhb {
 
@@ -47,6 +48,8 @@ struct SpectralPlan {
     int32_t n_cols;
     int32_t col[kMaxCols];
     int32_t lo[kMaxCols], hi[kMaxCols];   // bin range [lo, hi) of the column
+    int32_t redo_col;                     // >= 0: second pass -- only windows whose cell in this column holds the
+                                          // redo marker (psd_entropy.cuh) are evaluated; -1: every window
 };
 
 __device__ __forceinline__ void put(const SpectralPlan& P, int64_t idx, double v) {
@@ -73,8 +76,7 @@ __global__ void __launch_bounds__(kWarps * 32) window_spectral_kernel(const Spec
     __syncthreads();
 
     const int n_warps = blockDim.x >> 5;
-    for (int64_t w = static_cast<int64_t>(blockIdx.x) * n_warps + warp; w < P.total_windows;
-         w += static_cast<int64_t>(gridDim.x) * n_warps) {
+    auto do_window = [&](int64_t w) {
         const int64_t series = w / P.nw;
         const int64_t wi = w - series * P.nw;
         const float* src = P.x + series * P.series_stride + wi * P.S;
@@ -145,7 +147,7 @@ __global__ void __launch_bounds__(kWarps * 32) window_spectral_kernel(const Spec
         if (P.n_cols == 0) {                      // raw PSD rows
             for (int k = lane; k < P.nb; k += 32) put(P, obase + k * P.o_col, k == 0 ? dc : static_cast<double>(psd[k]));
             __syncwarp();
-            continue;
+            return;
         }
 
         // ---- reductions: total power first (relative power / entropy need it)
@@ -202,10 +204,50 @@ __global__ void __launch_bounds__(kWarps * 32) window_spectral_kernel(const Spec
                 const double p0 = dc / tot + 1e-30, qrest = (tot - dc) / tot;
                 hs += p0 * (qrest < 0.5 ? log1p(-qrest) : log(p0));
                 v = -hs;
+                if (tot > 0.0 && v < static_cast<double>(kToneEntropy) && p0 < 0.5) {    // noiseless tone: psd_entropy.cuh
+                    v = entropy_dominant_bin(
+                        psd, P.nb, dc, tot, lane, 32,
+                        [](float& b, int& a) {
+#pragma unroll
+                            for (int o = 16; o > 0; o >>= 1) {
+                                const float ob = __shfl_xor_sync(0xffffffffu, b, o);
+                                const int oa = __shfl_xor_sync(0xffffffffu, a, o);
+                                if (ob > b || (ob == b && oa < a)) {
+                                    b = ob;
+                                    a = oa;
+                                }
+                            }
+                        },
+                        [](double s) { return warp_sum(s); });
+                }
             }
             if (lane == 0) put(P, obase + j * P.o_col, v);
         }
         __syncwarp();
+    };
+
+    const int64_t first = static_cast<int64_t>(blockIdx.x) * n_warps + warp, stride = static_cast<int64_t>(gridDim.x) * n_warps;
+    if (P.redo_col < 0) {
+        for (int64_t w = first; w < P.total_windows; w += stride) do_window(w);
+    } else {
+        // second pass behind a kernel that left redo markers: a warp scans 32 windows at a time (one cell per lane, so
+        // the scan is not a chain of dependent loads) and evaluates the marked ones
+        for (int64_t g = first * 32; g < P.total_windows; g += stride * 32) {
+            const int64_t w = g + lane;
+            bool marked = false;
+            if (w < P.total_windows) {
+                const int64_t series = w / P.nw;
+                const int64_t cell = series * P.o_series + (w - series * P.nw) * P.o_window + P.redo_col * P.o_col;
+                marked = P.out_f32 ? reinterpret_cast<const uint32_t*>(P.out)[cell] == kRedoMarkF32
+                                   : reinterpret_cast<const unsigned long long*>(P.out)[cell] == kRedoMarkF64;
+            }
+            unsigned m = __ballot_sync(0xffffffffu, marked);
+            while (m) {
+                const int b = __ffs(m) - 1;
+                m &= m - 1;
+                do_window(g + b);
+            }
+        }
     }
 }
 
@@ -257,6 +299,7 @@ int32_t spectral_launch(const float* x, const mhb_windows* geom, double fs, cons
     P.o_window = o_window;
     P.o_col = o_col;
     P.n_cols = n_features;
+    P.redo_col = -1;
     for (int j = 0; j < n_features; ++j) {
         const int f = h_features[j];
         MHB_REQUIRE(f >= MHB_S_TOTAL_POWER && f <= MHB_S_ENTROPY, MHB_E_FEATURE, "%s: unknown spectral column %d", who, f);
@@ -289,7 +332,13 @@ int32_t spectral_launch(const float* x, const mhb_windows* geom, double fs, cons
         if (sf != -100) return sf;
         const int32_t s9 = spectral_w1920_try(x, geom, nw, P.bin_hz, P.col, P.lo, P.hi, n_features, out, out_f32,
                                               o_series, o_window, o_col, stream_v);
-        if (s9 != -100) return s9;
+        if (s9 != -100) {
+            // that kernel keeps no PSD rows, so it leaves the redo marker in the entropy cells of noiseless-tone windows
+            // (psd_entropy.cuh); the generic kernel below re-evaluates exactly those (a scan of one cell per window)
+            for (int j = 0; j < n_features && P.redo_col < 0; ++j)
+                if (P.col[j] == MHB_S_ENTROPY) P.redo_col = j;
+            if (s9 != MHB_OK || P.redo_col < 0) return s9;
+        }
     }
     // one warp per window, two N-point buffers per warp: pick the warps per CTA that pack the most warps on an SM
     const size_t shared_tab = sizeof(Cx<float>) * (static_cast<size_t>(P.N) + (P.even ? P.nb : 0));

@@ -126,6 +126,35 @@ def test_w1920_kernel_ragged_batches(n, monkeypatch):
         np.testing.assert_allclose(gen[s, :, 6], tab["spectral_entropy"], rtol=1e-5)
 
 
+@pytest.mark.parametrize("W,S,fs", [(500, 250, 50.0), (1920, 64, 64.0), (256, 128, 50.0), (75, 25, 50.0)])
+def test_noiseless_tone_entropy(W, S, fs):
+    """One bin (not bin 0) holds nearly all the power: H ~ 1e-5 .. 1e-1.  The float32 evaluation of p ln p next to p = 1
+    would be off by ~1e-7 absolute (1e-3 relative here); the kernels switch to the log1p form of psd_entropy.cuh -- the
+    W=1920 kernel through redo markers and a second pass of the generic kernel.  Tolerance: 1e-5 relative plus 1e-9
+    absolute (an exactly periodic tone has H ~ 1e-14 in float64, which is rounding noise of either transform)."""
+    import torch
+    from oracle import spectral as OS
+    from pymhealth_b200 import engine, spectral as SP
+    rng = np.random.default_rng(W)
+    small = 0
+    for trial in range(12):
+        n = W + S * int(rng.integers(3, 40)) + int(rng.integers(0, S))
+        f0 = rng.uniform(0.3, fs / 2 - 0.5)
+        if trial % 4 == 0:
+            f0 = round(f0 * W / fs) * fs / W            # exactly on a bin
+        off = [0.0, 0.0, 1.0, -0.02][trial % 4 if trial >= 4 else 0]
+        x = (off + 0.4 * np.sin(2 * np.pi * f0 * np.arange(n) / fs)).astype(np.float32)
+        want = OS.spectral_table(x, W, S, fs, [], None, None)["spectral_entropy"]
+        small += int(np.sum(want < 0.05))
+        for dt in (torch.float64, torch.float32):
+            tab = engine.window_table(torch.from_numpy(x[None]).cuda(), W, S,
+                                      [SP.total_power(fs).feature(), SP.spectral_entropy(fs).feature()], fs=fs, out_dtype=dt)
+            got = tab[0, :, 1].cpu().numpy().astype(np.float64)
+            tol = 1e-5 if dt is torch.float64 else 2e-7 + 1e-5          # + the rounding of a float32 cell
+            assert np.all(np.abs(got - want) <= tol * want + 1e-9), (trial, f0, off, np.abs(got - want).max())
+    assert small > 0            # the case above really occurred
+
+
 @pytest.mark.parametrize("W,S", [(36, 9), (64, 16), (90, 30), (96, 32), (100, 50), (120, 40), (128, 64), (256, 128), (384, 96),
                                  (1000, 500), (1024, 512), (75, 25)])
 def test_generic_kernel_window_lengths(W, S):

@@ -130,21 +130,37 @@ def main():
             got = rolling_apply(funcs)(x, 500, 250)
             tab = OS.spectral_table(x, 500, 250, fs, bands, plo, phi)
             tot = tab["total_power"]
+            why = []
             ok = np.all(np.abs(got[0] - tot) <= 1e-5 * np.maximum(tot, 1e-30))
+            if not ok:
+                why.append("total")
             for j in range(5):
-                ok = ok and np.all(np.abs(got[1 + j] - tab["band_power_%d" % j]) <= 1e-5 * np.maximum(tab["band_power_%d" % j], 1e-3 * tot) + 1e-30)
+                okj = np.all(np.abs(got[1 + j] - tab["band_power_%d" % j]) <= 1e-5 * np.maximum(tab["band_power_%d" % j], 1e-3 * tot) + 1e-30)
+                if not okj:
+                    e = np.abs(got[1 + j] - tab["band_power_%d" % j])
+                    i = int(np.argmax(e))
+                    why.append("band%d win %d got %.9g want %.9g tot %.9g" % (j, i, got[1 + j][i], tab["band_power_%d" % j][i], tot[i]))
+                ok = ok and okj
             psd_ref, freqs = OS.window_psd(x, 500, 250, fs)
             lidx, uidx = OS.first_index(freqs, plo), OS.first_index(freqs, phi)
             pb = got[7].astype(np.int64)
             wantb = lidx + np.argmax(psd_ref[:, lidx:uidx], axis=1)
             for i in np.nonzero(pb != wantb)[0]:
                 a_, b_ = psd_ref[i, pb[i]], psd_ref[i, wantb[i]]
-                ok = ok and abs(a_ - b_) <= 1e-5 * max(b_, 1e-3 * tot[i])
+                okp = abs(a_ - b_) <= 1e-5 * max(b_, 1e-3 * tot[i])
+                if not okp:
+                    why.append("peak win %d got bin %d (%.9g) want bin %d (%.9g)" % (i, pb[i], a_, wantb[i], b_))
+                ok = ok and okp
             if np.all(tot > 0):
-                ok = ok and np.allclose(got[9], tab["spectral_entropy"], rtol=1e-5, atol=1e-9)
+                oke = np.allclose(got[9], tab["spectral_entropy"], rtol=1e-5, atol=1e-9)
+                if not oke:
+                    e = np.abs(got[9] - tab["spectral_entropy"])
+                    i = int(np.argmax(e))
+                    why.append("entropy win %d got %.9g want %.9g" % (i, got[9][i], tab["spectral_entropy"][i]))
+                ok = ok and oke
             if not ok:
                 bad += 1
-                print("SPECTRAL-FAST MISMATCH n=%d bands=%s peak=(%g,%g)" % (n, bands, plo, phi))
+                print("SPECTRAL-FAST MISMATCH n=%d bands=%s peak=(%g,%g) %s" % (n, bands, plo, phi, "; ".join(why)))
         else:                  # non-uniform windows
             n = int(rng.integers(50, 5000))
             idx = np.cumsum(rng.integers(1, 5, n)).astype(np.int64)
