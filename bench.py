@@ -346,7 +346,7 @@ def run_b200_arm(args):
             # FP32 lane-instructions the transform needs at the very least: ~16e3 per window
             fp32_peak = 148 * 128 * (clocks or {}).get("sm_mhz", 1965.0) * 1e6 if clocks else 148 * 128 * 1965e6
             dominant["note"] = ("kernel 2 is FP32-issue-bound (a 250-point complex FFT + PSD reducers per 1,000 B window is >= ~16e3 "
-                                "lane-instructions; 100 %% FP32 issue would be ~35 %% of HBM peak), not HBM-bound; frac is its HBM "
+                                "lane-instructions; 100 % FP32 issue would be ~35 % of HBM peak), not HBM-bound; frac is its HBM "
                                 "fraction all the same.  kernel 1a (HBM-bound) is listed under 'kernels'.")
             dominant["fp32_issue_floor_frac"] = (windows_per_step * 16e3 / fp32_peak) / (ms_spec * 1e-3)
         line = {

@@ -20,7 +20,7 @@ def main():
     rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 0)
     bad = 0
     for case in range(ncases):
-        kind = case % 7
+        kind = case % 11
         if kind == 0:          # order statistics: geometries that hit the block paths (k <= 2, k >= 8) and the full sort
             g = int(rng.choice([16, 24, 32, 50, 64, 100, 125, 250, 256, 300]))
             k = int(rng.choice([1, 2, 2, 2, 3, 5, 8, 12, 30]))
@@ -161,6 +161,90 @@ def main():
             if not ok:
                 bad += 1
                 print("SPECTRAL-FAST MISMATCH n=%d bands=%s peak=(%g,%g) %s" % (n, bands, plo, phi, "; ".join(why)))
+        elif kind == 7:        # generic spectral kernel: random smooth window lengths (even and odd), tones and noise
+            fs = float(rng.choice([25.0, 50.0, 64.0, 100.0]))
+            W = int(rng.choice([36, 45, 48, 60, 64, 75, 80, 90, 96, 100, 120, 125, 128, 150, 160, 200, 243, 256, 320, 375, 384,
+                                512, 600, 625, 750, 1000, 1024]))
+            S = int(rng.integers(1, W + 1))
+            n = W + S * int(rng.integers(0, 30)) + int(rng.integers(0, S))
+            tt = np.arange(n) / fs
+            x = (rng.choice([0.0, 1.0]) + 0.4 * np.sin(2 * np.pi * rng.uniform(0.3, fs / 2 - 0.5) * tt) +
+                 rng.choice([0.0, 0.0, 0.05, 0.5]) * rng.standard_normal(n)).astype(np.float32)
+            lo_, hi_ = float(rng.uniform(0, fs / 4)), float(rng.uniform(fs / 4, fs / 2))
+            got = rolling_apply([SP.total_power(fs), SP.band_power(fs, lo_, hi_), SP.peak_bin(fs, lo_, hi_),
+                                 SP.spectral_entropy(fs)])(x, W, S)
+            tab = OS.spectral_table(x, W, S, fs, [(lo_, hi_)], lo_, hi_)
+            tot = tab["total_power"]
+            why = []
+            if not np.all(np.abs(got[0] - tot) <= 1e-5 * tot):
+                why.append("total")
+            if not np.all(np.abs(got[1] - tab["band_power_0"]) <= 1e-5 * np.maximum(tab["band_power_0"], 1e-3 * tot)):
+                why.append("band")
+            if not np.all(np.abs(got[3] - tab["spectral_entropy"]) <= 1e-5 * tab["spectral_entropy"] + 1e-9):
+                e = np.abs(got[3] - tab["spectral_entropy"])
+                i = int(np.argmax(e))
+                why.append("entropy win %d got %.9g want %.9g" % (i, got[3][i], tab["spectral_entropy"][i]))
+            psd_ref, freqs = OS.window_psd(x, W, S, fs)
+            lidx, uidx = OS.first_index(freqs, lo_), OS.first_index(freqs, hi_)
+            if uidx > lidx:
+                pb = got[2].astype(np.int64)
+                wantb = lidx + np.argmax(psd_ref[:, lidx:uidx], axis=1)
+                for i in np.nonzero(pb != wantb)[0]:
+                    a_, b_ = psd_ref[i, pb[i]], psd_ref[i, wantb[i]]
+                    if not abs(a_ - b_) <= 1e-5 * max(b_, 1e-3 * tot[i]):
+                        why.append("peak win %d got %d want %d" % (i, pb[i], wantb[i]))
+            if why:
+                bad += 1
+                print("SPECTRAL-GENERIC MISMATCH W=%d S=%d n=%d fs=%g band=(%g,%g): %s" % (W, S, n, fs, lo_, hi_, "; ".join(why[:4])))
+        elif kind == 8:        # HRV time-domain metrics
+            from oracle import hrv as OH
+            from pymhealth_b200.heart import hrv
+            n = int(rng.integers(3, 200000))
+            nn = (800 + 60 * rng.standard_normal(n)).clip(300, 2000)
+            if rng.random() < 0.3:
+                nn = np.round(nn)
+            pairs = [("sdnn", hrv.sdnn(nn), OH.sdnn(nn)), ("rmssd", hrv.rmssd(nn), OH.rmssd(nn)), ("ssd", hrv.ssd(nn), OH.ssd(nn)),
+                     ("sdsd", hrv.sdsd(nn), OH.sdsd(nn)), ("pnn50", hrv.pnnx(nn, "ms", 50.0), OH.pnnx(nn, "ms", 50.0)),
+                     ("pnn20", hrv.pnnx(nn, "ms", 20.0), OH.pnnx(nn, "ms", 20.0))]
+            if n > 700:
+                pairs += [("sdann", hrv.sdann(nn, unit="ms"), OH.sdann(nn, unit="ms")),
+                          ("sdnni", hrv.sdnni(nn, unit="ms"), OH.sdnni(nn, unit="ms"))]
+            for nm, g_, w_ in pairs:
+                # ssd telescopes to nn[-1] - nn[0]: its rounding error scales with sum |diff|, not with the result
+                atol = 1e-12 * float(np.abs(np.diff(nn)).sum()) if nm == "ssd" else 1e-12
+                if not np.isclose(g_, w_, rtol=1e-9, atol=atol, equal_nan=True):
+                    bad += 1
+                    print("HRV MISMATCH n=%d %s got %.15g want %.15g" % (n, nm, g_, w_))
+        elif kind == 9:        # accelerometer elementwise
+            from oracle import accel as OA
+            from pymhealth_b200.inertial import accelerometer as acc
+            n = int(rng.integers(1, 300000))
+            dt = rng.choice([np.float32, np.float64])
+            x, y, z = (rng.standard_normal(n).astype(dt) for _ in range(3))
+            for nm, g_, w_ in [("roll", acc.roll(y, z), OA.roll(y, z)), ("pitch", acc.pitch(x, y, z), OA.pitch(x, y, z)),
+                               ("magnitude", acc.magnitude(x, y, z), OA.magnitude(x, y, z)),
+                               ("magnitude_dot", acc.magnitude_dot(x, y, z), OA.magnitude_dot(x, y, z))]:
+                tol = 1e-5 if dt is np.float32 else 1e-12
+                if np.shape(g_) != np.shape(w_) or not np.allclose(g_, w_, rtol=tol, atol=tol):
+                    bad += 1
+                    print("ACCEL MISMATCH n=%d %s %s" % (n, np.dtype(dt).name, nm))
+        elif kind == 10:       # haversine forms
+            from oracle import location as OLc
+            from pymhealth_b200.location import distance as D
+            n, m_ = int(rng.integers(1, 50000)), int(rng.integers(1, 40))
+            la1, la2 = rng.uniform(-89, 89, n), rng.uniform(-89, 89, n)
+            lo1, lo2 = rng.uniform(-180, 180, n), rng.uniform(-180, 180, n)
+            if rng.random() < 0.5:              # neighbouring fixes (1 m .. 1 km apart)
+                la2 = la1 + rng.normal(0, 1e-4, n)
+                lo2 = lo1 + rng.normal(0, 1e-4, n)
+            checks = [("elementwise", D.haversine_elementwise(la1, lo1, la2, lo2), OLc.haversine_elementwise(la1, lo1, la2, lo2)),
+                      ("vector", D.haversine_vector(la1[0], lo1[0], la2, lo2), OLc.haversine_vector(la1[0], lo1[0], la2, lo2)),
+                      ("outer", D.haversine_outer_product(la1[:m_], lo1[:m_], la2[:97], lo2[:97]),
+                       OLc.haversine_outer_product(la1[:m_], lo1[:m_], la2[:97], lo2[:97]))]
+            for nm, g_, w_ in checks:
+                if g_.shape != w_.shape or not np.allclose(g_, w_, rtol=1e-9, atol=1e-12):
+                    bad += 1
+                    print("HAVERSINE MISMATCH n=%d %s maxrel %.3g" % (n, nm, np.max(np.abs(g_ - w_) / np.maximum(w_, 1e-300))))
         else:                  # non-uniform windows
             n = int(rng.integers(50, 5000))
             idx = np.cumsum(rng.integers(1, 5, n)).astype(np.int64)
