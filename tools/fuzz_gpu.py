@@ -20,7 +20,7 @@ def main():
     rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 0)
     bad = 0
     for case in range(ncases):
-        kind = case % 11
+        kind = case % 15
         if kind == 0:          # order statistics: geometries that hit the block paths (k <= 2, k >= 8) and the full sort
             g = int(rng.choice([16, 24, 32, 50, 64, 100, 125, 250, 256, 300]))
             k = int(rng.choice([1, 2, 2, 2, 3, 5, 8, 12, 30]))
@@ -245,6 +245,87 @@ def main():
                 if g_.shape != w_.shape or not np.allclose(g_, w_, rtol=1e-9, atol=1e-12):
                     bad += 1
                     print("HAVERSINE MISMATCH n=%d %s maxrel %.3g" % (n, nm, np.max(np.abs(g_ - w_) / np.maximum(w_, 1e-300))))
+        elif kind == 11:       # complex128 FFT drop-in: lengths with prime factors <= 31, real and complex rows
+            from pymhealth_b200 import fft as F
+            n = int(np.prod(rng.choice([2, 2, 2, 3, 3, 5, 5, 7, 11, 13, 17, 19, 23, 29, 31], int(rng.integers(1, 6)))))
+            if n > 4096:
+                n = int(rng.integers(1, 700))
+                while max((p_ for p_ in range(2, n + 1) if n % p_ == 0 and all(p_ % q for q in range(2, p_))), default=1) > 31:
+                    n += 1
+            rows = int(rng.integers(1, 40))
+            a = rng.standard_normal((rows, n))
+            if rng.random() < 0.5:
+                a = a + 1j * rng.standard_normal((rows, n))
+            fwd, want = F.fft(a), np.fft.fft(a, axis=-1)
+            inv, wanti = F.ifft(a), np.fft.ifft(a, axis=-1)
+            scale = np.abs(want).max() + 1e-300
+            if np.abs(fwd - want).max() > 1e-12 * scale * max(1, np.log2(n)) or np.abs(inv - wanti).max() > 1e-12 * max(1, np.log2(n)) * (np.abs(wanti).max() + 1e-300):
+                bad += 1
+                print("FFT MISMATCH n=%d rows=%d cplx=%s err %.3g" % (n, rows, np.iscomplexobj(a), np.abs(fwd - want).max() / scale))
+        elif kind == 12:       # cluster label statistics
+            from oracle import location as OLc
+            from pymhealth_b200.location import distribution as DB
+            n = int(rng.integers(1, 200000))
+            lab = rng.integers(-1, int(rng.integers(0, 300)) + 1, n).astype(np.int64)
+            if rng.random() < 0.3:
+                lab = np.sort(lab)
+            g1, w1 = DB.num_clusters(lab), OLc.num_clusters(lab)
+            g2, w2 = DB.cluster_totals(lab), OLc.cluster_totals(lab)
+            g3, w3 = DB.cluster_entropy(lab), OLc.cluster_entropy(lab)
+            g4, w4 = DB.normalized_cluster_entropy(lab), OLc.normalized_cluster_entropy(lab)
+            same_tot = dict(g2) == dict(w2) if isinstance(w2, dict) else np.array_equal(np.asarray(g2), np.asarray(w2))
+            if g1 != w1 or not same_tot or not np.isclose(g3, w3, rtol=1e-9, atol=1e-12) or \
+                    not np.isclose(g4, w4, rtol=1e-9, atol=1e-12, equal_nan=True):
+                bad += 1
+                print("LABEL MISMATCH n=%d: %r %r | %r %r | %r %r" % (n, g1, w1, g3, w3, g4, w4))
+        elif kind == 13:       # whole-series forms: gradient, zero_crossings, slope_sum
+            from oracle import reducers as ORd
+            from pymhealth_b200.heart import ppg
+            n = int(rng.integers(2, 300000))
+            x = rng.standard_normal(n) * rng.choice([1.0, 100.0])
+            if rng.random() < 0.5:
+                x = x.astype(np.float32)
+            th = float(rng.choice([0.0, 0.1, 0.5]))
+            g_ = timedom.gradient(x)
+            w_ = np.gradient(x.astype(np.float64)) if x.dtype == np.float64 else ORd.gradient(x)
+            if not np.allclose(g_, w_, rtol=1e-6 if x.dtype == np.float32 else 1e-12, atol=1e-6 if x.dtype == np.float32 else 1e-12):
+                bad += 1
+                print("GRADIENT MISMATCH n=%d %s" % (n, x.dtype))
+            xz = x.copy()
+            xz[np.abs(xz) <= th] = 0
+            pos = xz > 0
+            if not np.array_equal(timedom.zero_crossings(x, th), np.logical_xor(pos[:-1], pos[1:])):
+                bad += 1
+                print("ZERO-CROSSINGS MISMATCH n=%d th=%g" % (n, th))
+            w = int(rng.integers(1, 64))
+            xs = x[:20000].astype(np.float64)
+            # ppg.py:28-42 restated: out[i] = sum(diff(x)[i-w:i]) for w <= i < len(x) - 1, zero elsewhere
+            dx = np.diff(xs)
+            cs = np.concatenate([[0.0], np.cumsum(dx)])
+            want = np.zeros(len(xs))
+            ii = np.arange(w, len(xs) - 1)
+            want[ii] = cs[ii] - cs[ii - w]
+            got = ppg.slope_sum(xs, w)
+            if got.shape != want.shape or not np.allclose(got, want, rtol=1e-9, atol=1e-9 * np.abs(xs).max()):
+                bad += 1
+                print("SLOPE-SUM MISMATCH n=%d w=%d" % (len(xs), w))
+        elif kind == 14:       # get_indices / indices_rolling_apply on an irregular integer index
+            from pymhealth_b200.util.windows import get_indices, indices_rolling_apply
+            n = int(rng.integers(2, 50000))
+            idx = np.cumsum(rng.integers(1, 1000, n)).astype(np.int64) + int(rng.integers(-10**6, 10**6))
+            wsize, wstep = int(rng.integers(1, 20000)), int(rng.integers(1, 20000))
+            gi, wi = get_indices(idx, wsize, wstep), OW.get_indices(idx, wsize, wstep)
+            if not np.array_equal(gi, wi):
+                bad += 1
+                print("GET-INDICES MISMATCH n=%d wsize=%d wstep=%d" % (n, wsize, wstep))
+            else:
+                x = rng.standard_normal(n)
+                minlen = int(rng.integers(1, 4))
+                got = indices_rolling_apply(np.var, minlen)(gi, x, minlen)
+                want = OW.indices_rolling("var", wi, x, minlen)
+                if not np.allclose(got, want, rtol=1e-9, atol=1e-12, equal_nan=True):
+                    bad += 1
+                    print("INDICES-ROLLING MISMATCH n=%d wsize=%d wstep=%d" % (n, wsize, wstep))
         else:                  # non-uniform windows
             n = int(rng.integers(50, 5000))
             idx = np.cumsum(rng.integers(1, 5, n)).astype(np.int64)
