@@ -108,6 +108,16 @@ int32_t mhb_window_stats_f32(const float* x, const mhb_windows* geom,
 int32_t mhb_window_stats_f64(const double* x, const mhb_windows* geom,
                              const int32_t* h_features, int32_t n_features, double zc_threshold,
                              const mhb_table* table, void* stream);
+/* The same statistics of magnitude(x, y, z) = sqrt(x**2 + y**2 + z**2) (inertial/accelerometer.py:198-225), the step
+ * the reference takes immediately before windowing tri-axial data, WITHOUT materialising the magnitude series: the
+ * three axes (same geometry) are combined while a stage is copied into shared memory.  Bit-identical to
+ * mhb_accel_elementwise(MAGNITUDE) followed by mhb_window_stats_*. */
+int32_t mhb_window_stats_magnitude_f32(const float* x, const float* y, const float* z, const mhb_windows* geom,
+                                       const int32_t* h_features, int32_t n_features, double zc_threshold,
+                                       const mhb_table* table, void* stream);
+int32_t mhb_window_stats_magnitude_f64(const double* x, const double* y, const double* z, const mhb_windows* geom,
+                                       const int32_t* h_features, int32_t n_features, double zc_threshold,
+                                       const mhb_table* table, void* stream);
 
 /* ---- kernel 1b: per-window order statistics / derivative features -----------------------
  * Replaces rolling_apply(np.median | np.percentile | stats.interquartile_range | stats.mode |

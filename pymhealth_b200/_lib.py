@@ -52,6 +52,10 @@ SIGNATURES = {
                                          C.POINTER(MhbTable), _vp]),
     "mhb_window_stats_f64": (C.c_int32, [_vp, C.POINTER(MhbWindows), _i32p, C.c_int32, C.c_double,
                                          C.POINTER(MhbTable), _vp]),
+    "mhb_window_stats_magnitude_f32": (C.c_int32, [_vp, _vp, _vp, C.POINTER(MhbWindows), _i32p, C.c_int32, C.c_double,
+                                                   C.POINTER(MhbTable), _vp]),
+    "mhb_window_stats_magnitude_f64": (C.c_int32, [_vp, _vp, _vp, C.POINTER(MhbWindows), _i32p, C.c_int32, C.c_double,
+                                                   C.POINTER(MhbTable), _vp]),
     "mhb_window_order_f32": (C.c_int32, [_vp, C.POINTER(MhbWindows), _i32p, _f64p, C.c_int32,
                                          C.POINTER(MhbTable), _vp]),
     "mhb_window_order_f64": (C.c_int32, [_vp, C.POINTER(MhbWindows), _i32p, _f64p, C.c_int32,

@@ -41,6 +41,8 @@ constexpr int kNPre = 6;         // S1..S4, LL, ZC get a running prefix when k >
 
 struct StatsPlan {
     const void* x;
+    const void* y;               // magnitude mode (accelerometer.py:198-225 fused into the staging copy): the series is
+    const void* z;               // sqrt(x^2 + y^2 + z^2) of three arrays of the same geometry; null otherwise
     int64_t series_len, series_stride, total_elems;
     int64_t nw, win_per_chunk;
     int32_t chunks_per_series;
@@ -48,6 +50,7 @@ struct StatsPlan {
     int32_t flush;               // finalize once this many windows are pending
     int32_t stage_elems;
     int32_t use_tma;
+    int32_t mag_staged;          // magnitude mode through the MAG = true kernels (float32): three arrays per stage slot
     double th;
     double inv_n;
     void* out;
@@ -151,6 +154,18 @@ __device__ __forceinline__ double round_down_threshold<double>(double th) {
     return th;
 }
 
+// sqrt(x**2 + y**2 + z**2) in the input type with every operation rounded, exactly as accel.cu's standalone kernel
+template <typename InT>
+__device__ __forceinline__ InT magnitude3(InT x, InT y, InT z);
+template <>
+__device__ __forceinline__ float magnitude3<float>(float x, float y, float z) {
+    return sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z)));
+}
+template <>
+__device__ __forceinline__ double magnitude3<double>(double x, double y, double z) {
+    return sqrt(__dadd_rn(__dadd_rn(__dmul_rn(x, x), __dmul_rn(y, y)), __dmul_rn(z, z)));
+}
+
 // Chunk / stage geometry.  Everything a stage needs is 32-bit arithmetic relative to the chunk start (a chunk is
 // at most 64 stages of <= 24 KB); the 64-bit quantities are folded once per CTA.
 template <typename InT>
@@ -198,8 +213,12 @@ __device__ __forceinline__ int wrap(int i, int n) { return i >= n ? i - n : i; }
 // ---------------------------------------------------------------------------------------------
 // GEO = 1: the hot geometry (cpb = 10, k = 2, hop = 1, TB = 25 -- W = 500 / S = 250 with 25-sample cells) with every
 // loop bound known at compile time; GEO = 0: bounds from the plan.
-template <typename InT, typename OutT, bool M4, bool TD, int MCELL /*0 = runtime m; -8 = 2 x float4*/, int GEO>
+// MAG = true: magnitude mode with the three axes staged by TMA side by side (x | y | z, stage_elems apart) and combined
+// as phase 1 reads them; MAG = false with P.y set: the guarded-copy path combines them while copying.
+template <typename InT, typename OutT, bool M4, bool TD, int MCELL /*0 = runtime m; -8 = 2 x float4*/, int GEO, bool MAG = false>
 __global__ void __launch_bounds__(kThreads, 3) window_stats_kernel(const StatsPlan P) {
+    static_assert(!MAG || (MCELL >= 0 && GEO == 0), "magnitude mode uses the scalar cells");
+    constexpr int SB = MAG ? 3 : 1;          // arrays per stage slot
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int tid = threadIdx.x;
     const int m = MCELL > 0 ? MCELL : (MCELL < 0 ? -MCELL : P.m);
@@ -210,7 +229,7 @@ __global__ void __launch_bounds__(kThreads, 3) window_stats_kernel(const StatsPl
     uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);                 // NS barriers (<= 8)
     unsigned char* ptr = smem_raw + 128;
     InT* stage_buf = reinterpret_cast<InT*>(ptr);
-    ptr += static_cast<size_t>(P.NS) * P.stage_elems * sizeof(InT);
+    ptr += static_cast<size_t>(P.NS) * SB * P.stage_elems * sizeof(InT);
     const int ncell_max = g_TB * g_cpb;
     Part cell, ring;
     if (g_cpb > 1) ptr = cell.carve(ptr, ncell_max);
@@ -235,6 +254,24 @@ __global__ void __launch_bounds__(kThreads, 3) window_stats_kernel(const StatsPl
     ChunkDesc<InT> ck;
     ck.set(P, series_base, chunk_s0);
     const InT* xck = xg + ck.goff0;                       // chunk start
+    const InT* yck = MAG ? reinterpret_cast<const InT*>(P.y) + ck.goff0 : nullptr;
+    const InT* zck = MAG ? reinterpret_cast<const InT*>(P.z) + ck.goff0 : nullptr;
+    // thread 0: one expect_tx for the whole slot, one bulk copy per array
+    auto issue_stage = [&](int sl, const StageDesc<InT>& sd) {
+        InT* dst = stage_buf + static_cast<size_t>(sl) * SB * P.stage_elems;
+        const uint32_t bytes = sd.n_load * sizeof(InT);
+        mbar_arrive_expect_tx(&full[sl], SB * bytes);
+        bulk_g2s(dst, xck + (sd.rel - sd.lead), bytes, &full[sl]);
+        if (MAG) {
+            bulk_g2s(dst + P.stage_elems, yck + (sd.rel - sd.lead), bytes, &full[sl]);
+            bulk_g2s(dst + 2 * P.stage_elems, zck + (sd.rel - sd.lead), bytes, &full[sl]);
+        }
+    };
+    // sample i of a staged array: the magnitude of the three staged axes in magnitude mode
+    auto ld = [&](const InT* q, int i) -> InT {
+        if (MAG) return magnitude3<InT>(q[i], q[i + P.stage_elems], q[i + 2 * P.stage_elems]);
+        return q[i];
+    };
 
     if (tid == 0) {
         for (int i = 0; i < P.NS; ++i) mbar_init(&full[i], 1);
@@ -248,11 +285,7 @@ __global__ void __launch_bounds__(kThreads, 3) window_stats_kernel(const StatsPl
         for (int st = 0; st < P.NS && st < n_stages; ++st) {
             StageDesc<InT> d;
             d.set(P, ck, st, stage_samples, n_blocks - st * g_TB, g_TB);
-            if (d.tma) {
-                mbar_arrive_expect_tx(&full[st], d.n_load * sizeof(InT));
-                bulk_g2s(stage_buf + static_cast<size_t>(st) * P.stage_elems, xck + (d.rel - d.lead),
-                         d.n_load * sizeof(InT), &full[st]);
-            }
+            if (d.tma) issue_stage(st, d);
         }
     }
 
@@ -269,24 +302,54 @@ __global__ void __launch_bounds__(kThreads, 3) window_stats_kernel(const StatsPl
     for (int st = 0; st < n_stages; ++st) {
         StageDesc<InT> d;
         d.set(P, ck, st, stage_samples, n_blocks - st * g_TB, g_TB);
-        InT* buf = stage_buf + static_cast<size_t>(slot) * P.stage_elems;
+        InT* buf = stage_buf + static_cast<size_t>(slot) * SB * P.stage_elems;
         if (d.tma) {
             mbar_wait(&full[slot], parity);
         } else {
             // guarded cooperative copy: unaligned base pointer or the last few samples of the buffer
             const int n = d.cnt + d.has_next;
-            for (int i = tid; i < n; i += kThreads) buf[d.lead + i] = xck[d.rel + i];
+            if (MAG) {
+                const InT* ys = yck + d.rel;
+                const InT* zs = zck + d.rel;
+                for (int i = tid; i < n; i += kThreads) {
+                    buf[d.lead + i] = xck[d.rel + i];
+                    buf[d.lead + i + P.stage_elems] = ys[i];
+                    buf[d.lead + i + 2 * P.stage_elems] = zs[i];
+                }
+            } else if (P.y) {
+                // magnitude mode: the three axes are read straight from global memory (coalesced, four independent
+                // loads per axis in flight per thread) and only their magnitude is staged
+                const InT* yg = reinterpret_cast<const InT*>(P.y) + ck.goff0 + d.rel;
+                const InT* zg = reinterpret_cast<const InT*>(P.z) + ck.goff0 + d.rel;
+                const InT* xs = xck + d.rel;
+                InT* dstm = buf + d.lead;
+                int i = tid;
+                for (; i + 3 * kThreads < n; i += 4 * kThreads) {
+                    InT vx[4], vy[4], vz[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        vx[u] = __ldg(xs + i + u * kThreads);
+                        vy[u] = __ldg(yg + i + u * kThreads);
+                        vz[u] = __ldg(zg + i + u * kThreads);
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) dstm[i + u * kThreads] = magnitude3<InT>(vx[u], vy[u], vz[u]);
+                }
+                for (; i < n; i += kThreads) dstm[i] = magnitude3<InT>(xs[i], yg[i], zg[i]);
+            } else {
+                for (int i = tid; i < n; i += kThreads) buf[d.lead + i] = xck[d.rel + i];
+            }
             __syncthreads();
         }
         const InT* s = buf + d.lead;
-        if (st == 0) c = static_cast<double>(s[0]);
+        if (st == 0) c = static_cast<double>(ld(s, 0));
 
         // ---------------- phase 1: one cell per thread
         const int ncell = d.nblk * g_cpb;
         for (int ce = tid; ce < ncell; ce += kThreads) {
             const InT* p = s + ce * m;
             CellAcc<InT> a;
-            InT prev = p[0];
+            InT prev = ld(p, 0);
             a.mn = prev;
             a.mx = prev;
             float pos_prev = (TD && prev > th) ? 1.f : 0.f;
@@ -316,7 +379,7 @@ __global__ void __launch_bounds__(kThreads, 3) window_stats_kernel(const StatsPl
             } else if (MCELL > 0) {
 #pragma unroll
                 for (int i = 1; i < (MCELL > 0 ? MCELL : 1); ++i) {
-                    const InT v = p[i];
+                    const InT v = ld(p, i);
                     accum_moments<InT, M4>(a, v, c);
                     if (TD) {
                         const float pos = v > th ? 1.f : 0.f;
@@ -328,7 +391,7 @@ __global__ void __launch_bounds__(kThreads, 3) window_stats_kernel(const StatsPl
             } else {
 #pragma unroll 4
                 for (int i = 1; i < m; ++i) {
-                    const InT v = p[i];
+                    const InT v = ld(p, i);
                     accum_moments<InT, M4>(a, v, c);
                     if (TD) {
                         const float pos = v > th ? 1.f : 0.f;
@@ -340,7 +403,7 @@ __global__ void __launch_bounds__(kThreads, 3) window_stats_kernel(const StatsPl
             }
             float llb = 0.f, zcb = 0.f;
             if (TD && (ce + 1 < ncell || d.has_next)) {
-                const InT nx = p[m];
+                const InT nx = ld(p, m);
                 llb = fabsf(static_cast<float>(nx - prev));
                 zcb = ((nx > th) != (prev > th)) ? 1.f : 0.f;
             }
@@ -367,10 +430,7 @@ __global__ void __launch_bounds__(kThreads, 3) window_stats_kernel(const StatsPl
         if (tid == 0 && st + P.NS < n_stages) {
             StageDesc<InT> nd;
             nd.set(P, ck, st + P.NS, stage_samples, n_blocks - (st + P.NS) * g_TB, g_TB);
-            if (nd.tma) {
-                mbar_arrive_expect_tx(&full[slot], nd.n_load * sizeof(InT));
-                bulk_g2s(buf, xck + (nd.rel - nd.lead), nd.n_load * sizeof(InT), &full[slot]);
-            }
+            if (nd.tma) issue_stage(slot, nd);
         }
         if (++slot == P.NS) {
             slot = 0;
@@ -633,6 +693,21 @@ cudaError_t launch_with_cell(const StatsPlan& P, int mt, dim3 grid, size_t smem,
         kern<<<grid, kThreads, smem, stream>>>(P);                                                      \
         return cudaGetLastError();                                                                      \
     }
+    if (P.y && P.mag_staged) {
+        if constexpr (sizeof(InT) == 4) {
+#define MHB_LAUNCH_MAG(MC)                                                                              \
+    {                                                                                                   \
+        auto kern = window_stats_kernel<InT, OutT, M4, TD, MC, 0, true>;                                \
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        if (e != cudaSuccess) return e;                                                                 \
+        kern<<<grid, kThreads, smem, stream>>>(P);                                                      \
+        return cudaGetLastError();                                                                      \
+    }
+            if (mt == 25) MHB_LAUNCH_MAG(25)
+            MHB_LAUNCH_MAG(0)
+#undef MHB_LAUNCH_MAG
+        }
+    }
     if (mt == -8) {
         if constexpr (sizeof(InT) == 4) MHB_LAUNCH(-8, 0)
     }
@@ -649,7 +724,8 @@ cudaError_t launch_with_cell(const StatsPlan& P, int mt, dim3 grid, size_t smem,
 
 template <typename InT>
 int32_t window_stats_impl(const InT* x, const mhb_windows* geom, const int32_t* h_features, int32_t n_features,
-                          double zc_threshold, const mhb_table* table, void* stream_v) {
+                          double zc_threshold, const mhb_table* table, void* stream_v, const InT* y = nullptr,
+                          const InT* z = nullptr) {
     MHB_REQUIRE(geom && table, MHB_E_ARG, "window_stats: null geometry/table");
     MHB_REQUIRE(geom->wsize >= 1 && geom->wstep >= 1, MHB_E_ARG, "window_stats: wsize and wstep must be >= 1");
     MHB_REQUIRE(geom->n_series >= 0 && geom->series_len >= 0 && geom->series_stride >= geom->series_len,
@@ -670,8 +746,11 @@ int32_t window_stats_impl(const InT* x, const mhb_windows* geom, const int32_t* 
     const int64_t nw = n_windows_host(geom->series_len, geom->wsize, geom->wstep);
     if (nw == 0 || geom->n_series == 0 || n_features == 0) return MHB_OK;
     MHB_REQUIRE(x && table->out, MHB_E_ARG, "window_stats: null data/output pointer");
+    MHB_REQUIRE((y == nullptr) == (z == nullptr), MHB_E_ARG, "window_stats: magnitude mode takes both y and z");
     P.n_features = n_features;
     P.x = x;
+    P.y = y;
+    P.z = z;
     P.series_len = geom->series_len;
     P.series_stride = geom->series_stride;
     P.total_elems = (geom->n_series - 1) * geom->series_stride + geom->series_len;
@@ -688,6 +767,9 @@ int32_t window_stats_impl(const InT* x, const mhb_windows* geom, const int32_t* 
     // block size: a divisor of gcd(W, S) small enough for one stage, with k + hop bounded
     int64_t g = gcd64(P.W, P.S);
     constexpr int64_t kMaxStageBytes = 25 * 1024;      // 25 blocks of 250 float32 samples fit one stage
+    // magnitude mode, float32: the three axes are staged side by side (a third of the stage budget each, scalar cells)
+    const bool mag_staged = y != nullptr && sizeof(InT) == 4 && getenv("MHB_MAG_COPY") == nullptr;
+    P.mag_staged = mag_staged ? 1 : 0;
     const int64_t max_block = kMaxStageBytes / static_cast<int64_t>(sizeof(InT));
     if (g > max_block) {
         int64_t best = 1;
@@ -700,11 +782,13 @@ int32_t window_stats_impl(const InT* x, const mhb_windows* geom, const int32_t* 
     }
     P.g = static_cast<int32_t>(g);
     const int64_t k64 = P.W / g, hop64 = P.S / g;
+    MHB_REQUIRE(!(y && k64 + hop64 > 1024), MHB_E_UNSUPPORTED,
+                "window_stats: magnitude mode needs gcd(wsize, wstep) >= (wsize + wstep) / 1024");
     if (k64 + hop64 > 1024)        // e.g. co-prime W and S: no block sharing to exploit, evaluate every window directly
         return window_stats_direct<InT>(x, geom, nw, h_features, n_features, zc_threshold, table, stream_v);
     P.k = static_cast<int32_t>(k64);
     P.hop = static_cast<int32_t>(hop64);
-    const CellChoice cc = choose_cell(g, sizeof(InT) == 4 && geom->series_stride % 4 == 0);
+    const CellChoice cc = choose_cell(g, sizeof(InT) == 4 && geom->series_stride % 4 == 0 && !mag_staged);
     P.m = cc.m;
     P.cpb = static_cast<int32_t>(g / cc.m);
     int64_t tb = P.cpb <= kThreads ? kThreads / P.cpb : 1;
@@ -727,13 +811,21 @@ int32_t window_stats_impl(const InT* x, const mhb_windows* geom, const int32_t* 
     P.NS = P.k > kDirectK ? 1 : 2;
     constexpr int A = 16 / sizeof(InT);
     P.stage_elems = ((P.TB * P.g + 1 + (A - 1) + A - 1) / A) * A + A;
-    P.use_tma = (reinterpret_cast<uintptr_t>(x) % 16 == 0) ? 1 : 0;
+    P.use_tma = (reinterpret_cast<uintptr_t>(x) % 16 == 0 && y == nullptr) ? 1 : 0;
+    if (mag_staged) {
+        P.use_tma = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(z)) % 16 == 0) ? 1 : 0;
+        // the same stage geometry as the single-array kernel (so the chunking, and with it every rounding, is the same),
+        // three arrays per slot, ONE slot: the two CTAs of an SM cover each other's copy latency (measured: 2.5 ms
+        // against 3.9 ms with two slots and one CTA per SM, tools/perf_magnitude.py)
+        P.NS = 1;
+    }
 
-    size_t smem = 128 + static_cast<size_t>(P.NS) * P.stage_elems * sizeof(InT);
+    size_t smem = 128 + static_cast<size_t>(P.NS) * (mag_staged ? 3 : 1) * P.stage_elems * sizeof(InT);
     if (P.cpb > 1) smem += partial_bytes(sizeof(InT), m4, td, P.TB * P.cpb);
     smem += partial_bytes(sizeof(InT), m4, td, P.RB);
     if (P.k > kDirectK) smem += sizeof(double) * kNPre * (P.RB + 1);
     smem += 64;
+    MHB_REQUIRE(!(y && smem > 220 * 1024), MHB_E_UNSUPPORTED, "window_stats: magnitude mode: window geometry too awkward");
     if (smem > 220 * 1024)           // ring + prefix arrays of an awkward (k, hop) do not fit: evaluate every window directly
         return window_stats_direct<InT>(x, geom, nw, h_features, n_features, zc_threshold, table, stream_v);
 
@@ -785,4 +877,20 @@ extern "C" int32_t mhb_window_stats_f64(const double* x, const mhb_windows* geom
                                         int32_t n_features, double zc_threshold, const mhb_table* table,
                                         void* stream) {
     return mhb::window_stats_impl<double>(x, geom, h_features, n_features, zc_threshold, table, stream);
+}
+
+// Fused pre-stage of SURVEY 8f-1: the statistics of magnitude(x, y, z) (inertial/accelerometer.py:198-225) without
+// materialising the magnitude series.  x, y, z share the geometry (same length, stride, series count).
+extern "C" int32_t mhb_window_stats_magnitude_f32(const float* x, const float* y, const float* z, const mhb_windows* geom,
+                                                  const int32_t* h_features, int32_t n_features, double zc_threshold,
+                                                  const mhb_table* table, void* stream) {
+    MHB_REQUIRE(y && z, MHB_E_ARG, "window_stats_magnitude: null axis pointer");
+    return mhb::window_stats_impl<float>(x, geom, h_features, n_features, zc_threshold, table, stream, y, z);
+}
+
+extern "C" int32_t mhb_window_stats_magnitude_f64(const double* x, const double* y, const double* z, const mhb_windows* geom,
+                                                  const int32_t* h_features, int32_t n_features, double zc_threshold,
+                                                  const mhb_table* table, void* stream) {
+    MHB_REQUIRE(y && z, MHB_E_ARG, "window_stats_magnitude: null axis pointer");
+    return mhb::window_stats_impl<double>(x, geom, h_features, n_features, zc_threshold, table, stream, y, z);
 }

@@ -150,6 +150,60 @@ def window_table(x, wsize, wstep, features, zc_threshold=0.0, fs=1.0, out_dtype=
     return out[0] if was_1d else out
 
 
+def magnitude_window_table(x, y, z, wsize, wstep, features, zc_threshold=0.0, fs=1.0, out_dtype=None, out=None):
+    """Feature table of the windows of ``magnitude(x, y, z)`` (inertial/accelerometer.py:198-225 followed by
+    ``rolling_apply``) for tri-axial series of one geometry ([len] or [n_series, len] each).
+
+    The streaming family (kernel 1a) never materialises the magnitude: the axes are combined while a stage is copied
+    into shared memory (``mhb_window_stats_magnitude_*``).  Order-statistic and spectral columns need the series more
+    than once, so for them it is written to device memory once (``mhb_accel_elementwise``) and the ordinary kernels run
+    on it.  Results are bit-identical to ``window_table(magnitude(x, y, z), ...)``."""
+    torch = require_cuda()
+    lib = L.load()
+    wsize, wstep = int(wsize), int(wstep)
+    if wsize < 1 or wstep < 1:
+        raise ValueError("wsize and wstep must be >= 1")
+    tx, was_numpy, was_1d = to_device_series(x)
+    ty, _, _ = to_device_series(y)
+    tz, _, _ = to_device_series(z)
+    if not (tx.shape == ty.shape == tz.shape):
+        raise ValueError("x, y and z must have the same shape")
+    dt = torch.float32 if tx.dtype == ty.dtype == tz.dtype == torch.float32 else torch.float64
+    tx, ty, tz = (t.to(dt).contiguous() for t in (tx, ty, tz))
+    ns, n = tx.shape
+    nw = n_windows(n, wsize, wstep)
+    nf = len(features)
+    if out_dtype is None:
+        out_dtype = torch.float64 if was_numpy else torch.float32
+    if out is None:
+        out = torch.empty((ns, nw, nf), dtype=out_dtype, device=tx.device)
+    elif tuple(out.shape) != (ns, nw, nf):
+        raise ValueError("out has shape %s, expected %s" % (tuple(out.shape), (ns, nw, nf)))
+    if nw > 0 and ns > 0 and nf > 0:
+        stream = _stream_ptr(torch)
+        s_cols = [j for j, f in enumerate(features) if f.family == "stream"]
+        o_cols = [j for j, f in enumerate(features) if f.family != "stream"]
+        geom = L.MhbWindows(ns, n, n, wsize, wstep)
+        fn = lib.mhb_window_stats_magnitude_f32 if dt == torch.float32 else lib.mhb_window_stats_magnitude_f64
+        for run in _runs(s_cols):
+            tab = L.MhbTable(out.data_ptr() + run[0] * out.element_size(), 1 if out.dtype == torch.float32 else 0,
+                             out.stride(0), out.stride(1), out.stride(2))
+            ids = L.i32_array([features[j].fid for j in run])
+            L.check(fn(tx.data_ptr(), ty.data_ptr(), tz.data_ptr(), C.byref(geom), ids, len(run), float(zc_threshold),
+                       C.byref(tab), stream), "window_stats_magnitude")
+        if o_cols:
+            mag = torch.empty_like(tx)
+            L.check(lib.mhb_accel_elementwise(0, 1 if dt == torch.float64 else 0, tx.data_ptr(), ty.data_ptr(), tz.data_ptr(),
+                                              ns * n, mag.data_ptr(), stream), "magnitude")
+            for run in _runs(o_cols):
+                window_table(mag, wsize, wstep, [features[j] for j in run], zc_threshold=zc_threshold, fs=fs,
+                             out=out[:, :, run[0]:run[-1] + 1])
+    if was_numpy:
+        res = out.cpu().numpy()
+        return res[0] if was_1d else res
+    return out[0] if was_1d else out
+
+
 def n_index_windows(first, last, wstep, is_float):
     """len(np.arange(first, last, wstep)) without building the array (util/windows.py:175): numpy takes
     ceil((stop - start) / step) in float64 for floats and the exact integer count for integers."""

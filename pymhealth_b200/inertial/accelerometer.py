@@ -110,3 +110,40 @@ def magnitude_dot(x, y, z):
 @magnitude_dot.register(pd.DataFrame)
 def _pd_magnitude_dot(df, xcol: str = 'x', ycol: str = 'y', zcol: str = 'z'):
     return magnitude_dot(df[xcol].values, df[ycol].values, df[zcol].values)
+
+
+def rolling_magnitude(funcs, wsize=None, wstep: int = 1):
+    """``rolling_apply(funcs, wsize, wstep)(magnitude(x, y, z))`` in one step: returns a callable
+    ``(x, y, z, wsize=wsize, wstep=wstep)`` with rolling_apply's output forms (one reducer -> array, list / tuple ->
+    list, dict -> dict).  Streaming reducers (mean .. line_length) never materialise the magnitude series: the axes
+    are combined while kernel 1a stages its tile; results are bit-identical to the two-step form."""
+    from ..engine import magnitude_window_table
+    from ..reducers import resolve
+    from ..util.windows import _zc_threshold
+    if isinstance(funcs, dict):
+        names, flist, form = list(funcs.keys()), list(funcs.values()), "dict"
+    elif isinstance(funcs, (list, tuple)):
+        names, flist, form = None, list(funcs), "list"
+    else:
+        names, flist, form = None, [funcs], "one"
+    features = [resolve(f)[0] for f in flist]
+    fss = {f.fs for f in features if f.family == "spectral"}
+    if len(fss) > 1:
+        raise NotImplementedError("one sampling rate per rolling_magnitude call")
+    fs = fss.pop() if fss else 1.0
+
+    def magnitude_windows(x, y, z, wsize=wsize, wstep=wstep):
+        if wsize is None:
+            raise TypeError("wsize must be given (at rolling_magnitude() or at call time)")
+        arrs = [np.asarray(a) for a in (x, y, z)]
+        if any(a.ndim != 1 for a in arrs):
+            raise ValueError("rolling_magnitude takes three 1-D arrays")
+        if fss or features and any(f.family == "spectral" for f in features):
+            arrs = [a.astype(np.float32) for a in arrs]      # the spectral kernel computes in float32
+        tab = magnitude_window_table(arrs[0], arrs[1], arrs[2], int(wsize), int(wstep), features,
+                                     zc_threshold=_zc_threshold(features), fs=fs)
+        cols = [np.ascontiguousarray(tab[:, j]) for j in range(len(features))]
+        if form == "one":
+            return cols[0]
+        return dict(zip(names, cols)) if form == "dict" else cols
+    return magnitude_windows

@@ -141,3 +141,43 @@ def test_gradient_and_zero_crossings(ref_extra):
     np.testing.assert_array_equal(timedom.gradient(np.array([1.0, 4.0])), [3.0, 3.0])
     with pytest.raises(ValueError):
         timedom.gradient(np.array([1.0]))
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("W,S,n", [(500, 250, 40000), (128, 32, 9000), (1920, 64, 30000), (300, 300, 5000), (50, 7, 3000)])
+def test_rolling_magnitude_fused(dtype, W, S, n):
+    """window statistics of magnitude(x, y, z) with the magnitude formed inside kernel 1a's staging copy
+    -- bit-identical to materialising the magnitude and rolling over it, and equal to the oracle chain."""
+    from oracle import accel as OA, windows as OW
+    from pymhealth_b200 import synth, spectral as SP
+    from pymhealth_b200.generic import stats, timedom
+    from pymhealth_b200.inertial import accelerometer as acc
+    from pymhealth_b200.util import rolling_apply
+    x, y, z = (a.astype(dtype) for a in synth.accelerometer(17, n))
+    funcs = {"mean": np.mean, "std": np.std, "min": np.min, "max": np.max, "skew": stats.skewness, "kurt": stats.kurtosis,
+             "zc": timedom.zero_crossing_count, "ll": timedom.line_length, "median": np.median}
+    got = acc.rolling_magnitude(funcs, W, S)(x, y, z)
+    mag = acc.magnitude(x, y, z)
+    two_step = rolling_apply(funcs, W, S)(mag)
+    want_mag = OA.magnitude(x, y, z)
+    np.testing.assert_array_equal(mag, want_mag)
+    for name in funcs:
+        # the same kernel arithmetic on the same magnitudes; only the cell partition / pivot of the float64 partial sums
+        # may differ (bit-identical when the block size is not a multiple of 8, e.g. W=500 / S=250)
+        if name in ("min", "max", "zc", "median") or (W, S) == (500, 250):
+            np.testing.assert_array_equal(got[name], two_step[name], err_msg=name)
+        else:
+            np.testing.assert_allclose(got[name], two_step[name], rtol=1e-6 if name == "ll" else 1e-10, atol=1e-12, err_msg=name)
+    for name, oname in [("mean", "mean"), ("std", "std"), ("max", "max"), ("kurt", "kurtosis"), ("median", "median")]:
+        np.testing.assert_allclose(got[name], OW.rolling(oname, want_mag.astype(np.float64) if dtype is np.float64 else want_mag,
+                                                         W, S), rtol=1e-9, atol=1e-12, err_msg=name)
+    if dtype is np.float32 and W == 500:
+        h = acc.rolling_magnitude([np.mean, SP.spectral_entropy(50.0)], W, S)(x, y, z)
+        h2 = rolling_apply([np.mean, SP.spectral_entropy(50.0)], W, S)(mag)
+        np.testing.assert_array_equal(h[1], h2[1])
+    # one reducer form, ragged shapes
+    one = acc.rolling_magnitude(np.var)(x[:W + 3], y[:W + 3], z[:W + 3], W, S)
+    assert one.shape == (1,)
+    assert acc.rolling_magnitude(np.var, W, S)(x[:W - 1], y[:W - 1], z[:W - 1]).shape == (0,)
+    with pytest.raises(ValueError):
+        acc.rolling_magnitude(np.var, W, S)(x, y[:-1], z)
