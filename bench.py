@@ -289,6 +289,23 @@ def run_b200_arm(args):
         ms_order = o0.elapsed_time(o1) / 3
         del t_ord
 
+    # ---- also outside the step: kernel 1a in magnitude mode -- the same 10 streaming columns of
+    # magnitude(x, y, z), the three axis planes combined inside the TMA-staged tile (12 B of samples per magnitude)
+    ms_mag, mag_sub = None, min(32, nsub)
+    if rank == 0:
+        x3 = x.view(nsub, 3, n)[:mag_sub]
+        t_mag = torch.empty((mag_sub, nw, len(stream_f)), dtype=torch.float32, device=dev)
+        engine.magnitude_window_table(x3[:, 0], x3[:, 1], x3[:, 2], WSIZE, WSTEP, stream_f, out=t_mag)
+        o0, o1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        o0.record()
+        for _ in range(3):
+            engine.magnitude_window_table(x3[:, 0], x3[:, 1], x3[:, 2], WSIZE, WSTEP, stream_f, out=t_mag)
+        o1.record()
+        torch.cuda.synchronize()
+        ms_mag = o0.elapsed_time(o1) / 3
+        del t_mag
+
     # ---- end-to-end through the public host-buffer API (pinned host inputs, H2D + kernels + D2H per step)
     e2e_sub = min(args.e2e_subjects, nsub)
     numa_node = sharded.bind_host_to_device_numa(local)        # pinned buffers next to this GPU's PCIe root
@@ -366,7 +383,14 @@ def run_b200_arm(args):
                             "series": order_series, "ms_per_launch": ms_order,
                             "windows_per_s": order_series * nw / (ms_order * 1e-3) if ms_order else None,
                             "achieved": (order_series * n * 4 + order_series * nw * 8) / (ms_order * 1e-3) / 1e9 if ms_order else None,
-                            "unit": "GB/s"}},
+                            "unit": "GB/s"},
+                        "window_stats magnitude mode (not in the step)": {
+                            "kernel": "window_stats_kernel<MAG> (kernel 1a on magnitude(x, y, z), axes fused in the staged tile)",
+                            "bound": "hbm", "subjects": mag_sub, "ms_per_launch": ms_mag,
+                            "windows_per_s": mag_sub * nw / (ms_mag * 1e-3) if ms_mag else None,
+                            "achieved": (mag_sub * n * 12 + mag_sub * nw * len(stream_f) * 4) / (ms_mag * 1e-3) / 1e9 if ms_mag else None,
+                            "peak": peak, "unit": "GB/s",
+                            "frac": ((mag_sub * n * 12 + mag_sub * nw * len(stream_f) * 4) / (ms_mag * 1e-3) / 1e9 / peak) if ms_mag else None}},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(hx.numel() * 4),
                     "d2h_bytes_per_step": int(hout.numel() * 4), "subjects_per_step_per_gpu": e2e_sub,
                     "ms_per_step": float(e2e_ms.cpu()) / e2e_steps, "matches_resident_run": check_ok,

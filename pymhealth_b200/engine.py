@@ -169,8 +169,11 @@ def magnitude_window_table(x, y, z, wsize, wstep, features, zc_threshold=0.0, fs
     if not (tx.shape == ty.shape == tz.shape):
         raise ValueError("x, y and z must have the same shape")
     dt = torch.float32 if tx.dtype == ty.dtype == tz.dtype == torch.float32 else torch.float64
-    tx, ty, tz = (t.to(dt).contiguous() for t in (tx, ty, tz))
+    tx, ty, tz = (t.to(dt) for t in (tx, ty, tz))
+    if not (tx.stride() == ty.stride() == tz.stride()):
+        tx, ty, tz = (t.contiguous() for t in (tx, ty, tz))
     ns, n = tx.shape
+    row_stride = tx.stride(0) if ns > 1 else n       # e.g. the three axis planes of one [subjects, 3, len] tensor
     nw = n_windows(n, wsize, wstep)
     nf = len(features)
     if out_dtype is None:
@@ -183,7 +186,7 @@ def magnitude_window_table(x, y, z, wsize, wstep, features, zc_threshold=0.0, fs
         stream = _stream_ptr(torch)
         s_cols = [j for j, f in enumerate(features) if f.family == "stream"]
         o_cols = [j for j, f in enumerate(features) if f.family != "stream"]
-        geom = L.MhbWindows(ns, n, n, wsize, wstep)
+        geom = L.MhbWindows(ns, n, row_stride, wsize, wstep)
         fn = lib.mhb_window_stats_magnitude_f32 if dt == torch.float32 else lib.mhb_window_stats_magnitude_f64
         for run in _runs(s_cols):
             tab = L.MhbTable(out.data_ptr() + run[0] * out.element_size(), 1 if out.dtype == torch.float32 else 0,
@@ -192,8 +195,9 @@ def magnitude_window_table(x, y, z, wsize, wstep, features, zc_threshold=0.0, fs
             L.check(fn(tx.data_ptr(), ty.data_ptr(), tz.data_ptr(), C.byref(geom), ids, len(run), float(zc_threshold),
                        C.byref(tab), stream), "window_stats_magnitude")
         if o_cols:
-            mag = torch.empty_like(tx)
-            L.check(lib.mhb_accel_elementwise(0, 1 if dt == torch.float64 else 0, tx.data_ptr(), ty.data_ptr(), tz.data_ptr(),
+            cx, cy, cz = (t.contiguous() for t in (tx, ty, tz))
+            mag = torch.empty_like(cx)
+            L.check(lib.mhb_accel_elementwise(0, 1 if dt == torch.float64 else 0, cx.data_ptr(), cy.data_ptr(), cz.data_ptr(),
                                               ns * n, mag.data_ptr(), stream), "magnitude")
             for run in _runs(o_cols):
                 window_table(mag, wsize, wstep, [features[j] for j in run], zc_threshold=zc_threshold, fs=fs,
