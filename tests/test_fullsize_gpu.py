@@ -98,3 +98,18 @@ def test_config5_month_of_1hz_gps():
         sl = slice(k * day, (k + 1) * day)
         np.testing.assert_allclose(d[sl][1:], OL.arr_successive_distance(lat[sl], lon[sl])[1:], rtol=1e-9, atol=1e-12)
         np.testing.assert_allclose(rows[k, 2], OL.arr_location_variance(lat[sl], lon[sl]), rtol=1e-9)
+
+
+@pytest.mark.gpu
+def test_series_longer_than_2_31_samples():
+    """One 8.6 GB series (2^31 + 1,000,327 samples): 64-bit sample offsets INSIDE a series for kernels 1a, 1b and 2,
+    checked against the oracle at the head, across the 2^31 crossing and at the tail (tools/big_series_check.py)."""
+    import os
+    import runpy
+    import torch
+    if torch.cuda.mem_get_info()[0] < 24 * 2**30:
+        pytest.skip("needs ~20 GB of free HBM")
+    tool = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools", "big_series_check.py")
+    with pytest.raises(SystemExit) as ex:
+        runpy.run_path(tool, run_name="__main__")
+    assert ex.value.code == 0
