@@ -331,6 +331,46 @@ def run_b200_arm(args):
         dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
     e2e_value = world * e2e_sub * 3 * nw * e2e_steps / (float(e2e_ms.cpu()) * 1e-3)
 
+    # ---- BASELINE configs[1], reported beside the headline: ONE subject x 24 h x 3 axes (4.32 M samples per axis, 51,837
+    # axis-windows) -- a latency-sized job: resident (both kernels, 16 columns) and through the host-buffer API
+    single = None
+    if rank == 0:
+        n1 = 4_320_000
+        nw1 = engine.n_windows(n1, WSIZE, WSTEP)
+        x1 = x[:3, :n1]
+        t1 = torch.empty((3, nw1, nf), dtype=torch.float32, device=dev)
+
+        def step1():
+            engine.window_table(x1, WSIZE, WSTEP, stream_f, out=t1[:, :, :len(stream_f)])
+            engine.window_table(x1, WSIZE, WSTEP, spec_f, fs=FS, out=t1[:, :, len(stream_f):])
+        for _ in range(3):
+            step1()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        s0.record()
+        for _ in range(20):
+            step1()
+        s1.record()
+        torch.cuda.synchronize()
+        ms1 = s0.elapsed_time(s1) / 20
+        hx1 = torch.empty((3, n1), dtype=torch.float32).pin_memory()
+        hx1.copy_(x1)
+        ho1 = torch.empty((3, nw1, nf), dtype=torch.float32).pin_memory()
+        pipe1 = FeaturePipeline(feats, WSIZE, WSTEP, fs=FS, chunk_series=3)
+        for _ in range(2):
+            pipe1.run(hx1, ho1)
+        torch.cuda.synchronize()
+        w0_ = time.perf_counter()
+        for _ in range(10):
+            pipe1.run(hx1, ho1)
+        torch.cuda.synchronize()
+        e2e1 = (time.perf_counter() - w0_) / 10 * 1e3
+        single = {"workload": "BASELINE configs[1]: 1 subject x 24 h x 3 axes @ 50 Hz, W=500 S=250, 16 columns",
+                  "axis_windows": 3 * nw1, "resident_ms": ms1, "resident_windows_per_s": 3 * nw1 / (ms1 * 1e-3),
+                  "e2e_ms": e2e1, "e2e_windows_per_s": 3 * nw1 / (e2e1 * 1e-3),
+                  "h2d_bytes": int(hx1.numel() * 4), "d2h_bytes": int(ho1.numel() * 4)}
+        del t1, hx1, ho1
+
     # ---- the one collective of the design: gather per-subject summary rows (mean of every column over the week)
     summary = table.view(nsub, 3 * nw, nf).mean(dim=1)
     gather_ms = 0.0
@@ -396,6 +436,7 @@ def run_b200_arm(args):
                     "ms_per_step": float(e2e_ms.cpu()) / e2e_steps, "matches_resident_run": check_ok,
                     "api": "pymhealth_b200.pipeline.FeaturePipeline.run (pinned host in, pinned host out)",
                     "host_numa_node_rank0": numa_node},
+            "single_subject_24h": single,
             "gpu_launches": 2 * args.steps,
             "clocks": clocks,
             "gather_ms": gather_ms,
