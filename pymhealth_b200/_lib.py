@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmhb200.so")
+LIB_PATH = os.environ.get("MHB200_LIB") or os.path.join(_HERE, "libmhb200.so")      # MHB200_LIB: a development build
 
 # ---- feature ids (mirror of include/mhb200.h)
 F_MEAN, F_VAR, F_STD, F_MIN, F_MAX, F_DRANGE, F_SKEWNESS, F_KURTOSIS, F_KURTOSIS_EXCESS, \

@@ -30,10 +30,23 @@ namespace {
 using C = Cx<float>;
 
 constexpr int kW = 1920, kS = 64, kN = 960;
-constexpr int kBW = 4;                   // windows per batch
-constexpr int kT = 256;
+// Batch size / CTA shape: items per batch are 120 (A1), 80 (A2) and 49 (B) per window, so 6 windows on 320 threads give
+// 3 / 2 / 1 rounds at 75 % / 75 % / 92 % occupancy of the thread slots, two CTAs per SM.  Measured on config 4 (16 series):
+// 4 windows x 256 threads x 3 CTAs 8.83 ms, 5 x 320 x 2 8.32, 6 x 320 x 2 8.12, 7 x 384 x 2 8.51, 8 x 384 x 2 9.28.
+#ifndef MHB_W1920_BW
+#define MHB_W1920_BW 6
+#define MHB_W1920_T 320
+#define MHB_W1920_CTAS 2
+#endif
+constexpr int kBW = MHB_W1920_BW;        // windows per batch
+constexpr int kT = MHB_W1920_T;
+constexpr int kCtasPerSM = MHB_W1920_CTAS;
+static_assert(kBW * 49 <= kT && kBW * 80 <= 2 * kT && kBW * 32 <= kT,
+              "pass B is one round, pass A2 two rounds, pass C one warp per window");
 constexpr int kNS2 = 99;                 // complex stride between the n2 blocks of a window (96 used)
 constexpr int kWSTR = 10 * kNS2 + 1;     // complex stride between windows
+constexpr int kCS = 122;                 // complex stride between the c planes of the A1 -> A2 exchange layout (8 x 122 <= kWSTR)
+static_assert(8 * kCS <= kWSTR && kCS >= 120 && kCS % 16 == 10, "A1 -> A2 exchange layout");
 constexpr int kNP = 49;                  // pass-B threads per window: p = 0..48
 constexpr int kMaxCols = 32, kMaxSum = 4, kMaxArg = 2;
 constexpr int kTile = (kBW - 1) * kS + kW;      // 2112 floats
@@ -64,7 +77,7 @@ __device__ __forceinline__ uint32_t range_mask(int p, int lo, int hi) {
     return m;
 }
 
-__global__ void __launch_bounds__(kT, 3) spectral_w1920_kernel(const Plan1920 P) {
+__global__ void __launch_bounds__(kT, kCtasPerSM) spectral_w1920_kernel(const Plan1920 P) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);
     float* tiles = reinterpret_cast<float*>(smem_raw + 128);                // 2 x kTile
@@ -207,11 +220,15 @@ __global__ void __launch_bounds__(kT, 3) spectral_w1920_kernel(const Plan1920 P)
                 a[q] = {fmaf(v.x, 0.5f, mh), fmaf(v.y, 0.5f, mh)};
             }
             rdft<8>(a);
-            C* dst = buf + w * kWSTR + n2 * kNS2 + b;
+            // A1 -> A2 exchange layout [c][b][n2] with a c stride of 122 = 10 (mod 16): consecutive lanes (n2 fastest, then
+            // b) store consecutive complex words, and pass A2's lanes (n fastest, then c) read words congruent to their
+            // lane-linear index modulo the 16 64-bit bank pairs -- both conflict free (the [n2][k1] layout A2 writes
+            // and pass B reads is a different view of the same per-window region)
+            C* dst = buf + w * kWSTR + 10 * b + n2;
             const C* tw = tw96 + b * 8;
             dst[0] = a[0];
 #pragma unroll
-            for (int c = 1; c < 8; ++c) dst[c * 12] = cmul(a[c], tw[c]);
+            for (int c = 1; c < 8; ++c) dst[c * kCS] = cmul(a[c], tw[c]);
         }
         __syncthreads();
 
@@ -225,12 +242,14 @@ __global__ void __launch_bounds__(kT, 3) spectral_w1920_kernel(const Plan1920 P)
             C* blk0 = buf + wA * kWSTR + nA * kNS2;
             C* blk1 = buf + wB * kWSTR + nB * kNS2;
             if (has0) {
+                const C* src = buf + wA * kWSTR + cA * kCS + nA;
 #pragma unroll
-                for (int b = 0; b < 12; ++b) in0[b] = blk0[cA * 12 + b];
+                for (int b = 0; b < 12; ++b) in0[b] = src[10 * b];
             }
             if (has1) {
+                const C* src = buf + wB * kWSTR + cB * kCS + nB;
 #pragma unroll
-                for (int b = 0; b < 12; ++b) in1[b] = blk1[cB * 12 + b];
+                for (int b = 0; b < 12; ++b) in1[b] = src[10 * b];
             }
             __syncthreads();
             if (has0) {
@@ -515,7 +534,7 @@ int32_t spectral_w1920_try(const float* x, const mhb_windows* geom, int64_t nw, 
     cudaError_t e = cudaFuncSetAttribute(spectral_w1920_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          static_cast<int>(smem));
     if (e != cudaSuccess) return cuda_status(e, "spectral_w1920 attr");
-    int64_t ctas = static_cast<int64_t>(kNumSMs) * 3;
+    int64_t ctas = static_cast<int64_t>(kNumSMs) * kCtasPerSM;
     if (ctas > P.total_batches) ctas = P.total_batches;
     spectral_w1920_kernel<<<static_cast<unsigned>(ctas), kT, smem, static_cast<cudaStream_t>(stream)>>>(P);
     return cuda_status(cudaGetLastError(), "spectral_w1920 launch");
