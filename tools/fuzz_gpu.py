@@ -20,7 +20,7 @@ def main():
     rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 0)
     bad = 0
     for case in range(ncases):
-        kind = case % 15
+        kind = case % 17
         if kind == 0:          # order statistics: geometries that hit the block paths (k <= 2, k >= 8) and the full sort
             g = int(rng.choice([16, 24, 32, 50, 64, 100, 125, 250, 256, 300]))
             k = int(rng.choice([1, 2, 2, 2, 3, 5, 8, 12, 30]))
@@ -326,6 +326,47 @@ def main():
                 if not np.allclose(got, want, rtol=1e-9, atol=1e-12, equal_nan=True):
                     bad += 1
                     print("INDICES-ROLLING MISMATCH n=%d wsize=%d wstep=%d" % (n, wsize, wstep))
+        elif kind == 15:       # spectral W = 1920 / S = 64 kernel: ragged batches, tones (redo pass), several columns
+            fs = 64.0
+            n = 1920 + 64 * int(rng.integers(0, 60)) + int(rng.integers(0, 64))
+            tt = np.arange(n) / fs
+            x = (rng.choice([0.0, 2.0]) + 0.4 * np.sin(2 * np.pi * rng.uniform(0.3, 30) * tt) +
+                 rng.choice([0.0, 0.0, 0.05, 0.5]) * rng.standard_normal(n)).astype(np.float32)
+            lo_, hi_ = float(rng.uniform(0, 8)), float(rng.uniform(8, 32))
+            got = rolling_apply([SP.total_power(fs), SP.band_power(fs, lo_, hi_), SP.peak_bin(fs, lo_, hi_),
+                                 SP.spectral_entropy(fs), SP.relative_band_power(fs, 0.0, lo_)])(x, 1920, 64)
+            tab = OS.spectral_table(x, 1920, 64, fs, [(lo_, hi_), (0.0, lo_)], lo_, hi_)
+            tot = tab["total_power"]
+            ok = np.all(np.abs(got[0] - tot) <= 1e-5 * tot)
+            ok = ok and np.all(np.abs(got[1] - tab["band_power_0"]) <= 1e-5 * np.maximum(tab["band_power_0"], 1e-3 * tot))
+            ok = ok and np.all(np.abs(got[4] - tab["rel_band_power_1"]) <= 1e-5 * np.maximum(tab["rel_band_power_1"], 1e-3))
+            ok = ok and np.all(np.abs(got[3] - tab["spectral_entropy"]) <= 1e-5 * tab["spectral_entropy"] + 1e-9)
+            psd_ref, freqs = OS.window_psd(x, 1920, 64, fs)
+            lidx, uidx = OS.first_index(freqs, lo_), OS.first_index(freqs, hi_)
+            pb = got[2].astype(np.int64)
+            wantb = lidx + np.argmax(psd_ref[:, lidx:uidx], axis=1)
+            for i in np.nonzero(pb != wantb)[0]:
+                a_, b_ = psd_ref[i, pb[i]], psd_ref[i, wantb[i]]
+                ok = ok and abs(a_ - b_) <= 1e-5 * max(b_, 1e-3 * tot[i])
+            if not ok:
+                bad += 1
+                print("SPECTRAL-W1920 MISMATCH n=%d band=(%g,%g)" % (n, lo_, hi_))
+        elif kind == 16:       # fused magnitude statistics against the two-step form and the oracle
+            from oracle import accel as OA
+            from pymhealth_b200.inertial import accelerometer as acc
+            g = int(rng.choice([10, 25, 32, 50, 64, 100, 125, 250]))
+            k, hop = int(rng.integers(1, 12)), int(rng.integers(1, 6))
+            W, S = g * k, g * hop
+            n = W + S * int(rng.integers(0, 60)) + int(rng.integers(0, S))
+            dt = rng.choice([np.float32, np.float64])
+            x, y, z = ((rng.standard_normal(n) + o).astype(dt) for o in (0.0, 0.3, 1.0))
+            got = acc.rolling_magnitude([np.mean, np.std, np.min, stats.kurtosis, timedom.line_length], W, S)(x, y, z)
+            mag = OA.magnitude(x, y, z)
+            for g_, nm in zip(got, ["mean", "std", "min", "kurtosis", "line_length"]):
+                want = OW.rolling(nm, mag, W, S)
+                if not np.allclose(g_, want, rtol=1e-6 if nm == "line_length" else 1e-9, atol=1e-12):
+                    bad += 1
+                    print("MAGNITUDE MISMATCH W=%d S=%d n=%d %s %s" % (W, S, n, np.dtype(dt).name, nm))
         else:                  # non-uniform windows
             n = int(rng.integers(50, 5000))
             idx = np.cumsum(rng.integers(1, 5, n)).astype(np.int64)
