@@ -199,17 +199,12 @@ __global__ void __launch_bounds__(kT, kCtasPerSM) spectral_w1920_kernel(const Pl
             const int w = it / 120, r = it - w * 120;
             if (w >= nwin) continue;
             const int b = r / 10, n2 = r - b * 10;
-            // pivot of the window: the mean of 16 samples spread over it (z[120 a], a = 0..7).  Every thread of the
-            // window reads the same addresses (broadcasts), so all agree bit for bit; any value near the mean works,
-            // bin 0 is restored exactly in pass B.
+            // pivot of the window: the mean of 4 samples from its two halves.  Every thread of the window reads the same
+            // addresses (broadcasts), so all agree bit for bit; any value near the mean works (it only keeps a large DC
+            // out of the float32 dynamic range), bin 0 is restored exactly in pass B.
             const float2* zw = reinterpret_cast<const float2*>(tile + w * kS);
-            float m = 0.f;
-#pragma unroll
-            for (int q = 0; q < 8; ++q) {
-                const float2 v = zw[120 * q];
-                m += v.x + v.y;
-            }
-            m *= (1.0f / 16.0f);
+            const float2 pa = zw[240], pb2 = zw[720];
+            const float m = ((pa.x + pa.y) + (pb2.x + pb2.y)) * 0.25f;
             if (r == 0) piv[w] = m;
             const float mh = -0.5f * m;
             const float2* z = zw + 10 * b + n2;
