@@ -441,14 +441,11 @@ __global__ void __launch_bounds__(kThreadsF, 3) spectral_fast_kernel(const FastP
             // ---- pass A (warps 0-4): 25-point DFTs of the stride-10 subsequences, inter-pass twiddle, exchange
             if (act && live) {
                 const int n2 = role;
-                // pivot of the transform: a 16-sample estimate of the window mean (any value near the mean works:
+                // pivot of the transform: a 4-sample estimate of the window mean (any value near the mean works:
                 // bin 0 is restored exactly in pass B; the pivot only keeps a large DC out of the float32 dynamic
-                // range).  Every thread of the window reads the same 16 samples, so they agree bit for bit.
+                // range).  Every thread of the window reads the same 4 samples, so they agree bit for bit.
                 const float* xw = tile + w * kS;
-                float m = 0.f;
-#pragma unroll
-                for (int j = 0; j < 16; ++j) m += xw[15 + 31 * j];
-                m *= (1.0f / 16.0f);
+                const float m = ((xw[62] + xw[187]) + (xw[312] + xw[437])) * 0.25f;
                 const float mh = -0.5f * m;
                 const float2* z = reinterpret_cast<const float2*>(xw) + n2;
                 C a[25];
