@@ -20,7 +20,7 @@ def main():
     rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 0)
     bad = 0
     for case in range(ncases):
-        kind = case % 17
+        kind = case % 18
         if kind == 0:          # order statistics: geometries that hit the block paths (k <= 2, k >= 8) and the full sort
             g = int(rng.choice([16, 24, 32, 50, 64, 100, 125, 250, 256, 300]))
             k = int(rng.choice([1, 2, 2, 2, 3, 5, 8, 12, 30]))
@@ -367,6 +367,42 @@ def main():
                 if not np.allclose(g_, want, rtol=1e-6 if nm == "line_length" else 1e-9, atol=1e-12):
                     bad += 1
                     print("MAGNITUDE MISMATCH W=%d S=%d n=%d %s %s" % (W, S, n, np.dtype(dt).name, nm))
+        elif kind == 17:       # engine plumbing: strided multi-series views (aligned or not), families interleaved in the
+            import torch       # column order, float32 / float64 tables
+            from pymhealth_b200 import engine
+            fs = 50.0
+            g = int(rng.choice([16, 25, 50, 64, 125, 250]))
+            k, hop = int(rng.integers(1, 5)), int(rng.integers(1, 4))
+            W, S = g * k, g * hop
+            if W % 2 or W < 8:
+                W, S = 500, 250
+            ns = int(rng.integers(1, 6))
+            n = W + S * int(rng.integers(0, 50)) + int(rng.integers(0, S))
+            off = int(rng.integers(0, 7))
+            big = torch.from_numpy((rng.standard_normal((ns, n + 11)) + 1.0).astype(np.float32)).cuda()
+            xv = big[:, off:off + n]
+            pool = [("mean", stats.mean.feature()), ("median", stats.median.feature()), ("S:total", SP.total_power(fs).feature()),
+                    ("kurtosis", stats.kurtosis.feature()), ("S:entropy", SP.spectral_entropy(fs).feature()),
+                    ("max", stats.dmax.feature()), ("percentile", stats.percentile.feature(25.0)),
+                    ("line_length", timedom.line_length.feature()), ("S:band", SP.band_power(fs, 1.0, 9.0).feature())]
+            order = rng.permutation(len(pool))[:int(rng.integers(1, len(pool) + 1))]
+            feats = [pool[i] for i in order]
+            odt = torch.float64 if rng.random() < 0.5 else torch.float32
+            tab = engine.window_table(xv, W, S, [f for _, f in feats], fs=fs, out_dtype=odt).cpu().numpy().astype(np.float64)
+            xh = xv.cpu().numpy()
+            ftol = 1e-9 if odt is torch.float64 else 3e-7
+            for si in range(ns):
+                sp = OS.spectral_table(xh[si], W, S, fs, [(1.0, 9.0)], None, None)
+                for c, (nm, _) in enumerate(feats):
+                    if nm.startswith("S:"):
+                        want = {"S:total": sp["total_power"], "S:entropy": sp["spectral_entropy"], "S:band": sp["band_power_0"]}[nm]
+                        okc = np.all(np.abs(tab[si, :, c] - want) <= (1e-5 + ftol) * np.maximum(np.abs(want), 1e-3 * sp["total_power"] if nm != "S:entropy" else 0) + 1e-9)
+                    else:
+                        want = OW.rolling(nm, xh[si], W, S, 25.0 if nm == "percentile" else None)
+                        okc = np.allclose(tab[si, :, c], want, rtol=max(ftol, 1e-6 if nm == "line_length" else 1e-9), atol=1e-12 if odt is torch.float64 else 1e-6)
+                    if not okc:
+                        bad += 1
+                        print("ENGINE MISMATCH W=%d S=%d ns=%d n=%d off=%d %s col %d (%s) of %s" % (W, S, ns, n, off, odt, c, nm, [a for a, _ in feats]))
         else:                  # non-uniform windows
             n = int(rng.integers(50, 5000))
             idx = np.cumsum(rng.integers(1, 5, n)).astype(np.int64)
