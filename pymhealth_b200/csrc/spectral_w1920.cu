@@ -13,8 +13,8 @@
 //                           (k, N - k) pairs of the real-input untangling -- so |X|^2, the per-thread totals, the
 //                           entropy records and the masked band / arg-max partials are formed on REGISTER values
 //   C   warp w:             merges the 49 partial records of window w with shuffles and stores the columns.
-// A CTA owns a batch of 4 consecutive windows of one series (2112 samples, one bulk TMA copy, double buffered); 97 % of a
-// tile overlaps the next batch's, so the re-reads are L2 hits.  Pivot removal / exact bin 0 / 1/2 prescale as in
+// A CTA (320 threads, two per SM) owns a batch of 6 consecutive windows of one series (2240 samples, one bulk TMA copy,
+// double buffered); 97 % of a tile overlaps the next batch's, so the re-reads are L2 hits.  Pivot removal / exact bin 0 / 1/2 prescale as in
 // spectral_fast.cu.  Deterministic: every reduction has a fixed order.
 #include <cmath>
 #include <cstdlib>
@@ -49,7 +49,7 @@ constexpr int kCS = 122;                 // complex stride between the c planes 
 static_assert(8 * kCS <= kWSTR && kCS >= 120 && kCS % 16 == 10, "A1 -> A2 exchange layout");
 constexpr int kNP = 49;                  // pass-B threads per window: p = 0..48
 constexpr int kMaxCols = 32, kMaxSum = 4, kMaxArg = 2;
-constexpr int kTile = (kBW - 1) * kS + kW;      // 2112 floats
+constexpr int kTile = (kBW - 1) * kS + kW;      // 2240 floats for 6 windows
 constexpr int kMaskStride = 52;
 
 struct Plan1920 {
