@@ -60,6 +60,23 @@ def test_product_fails_loudly_without_cuda():
     from pymhealth_b200.location import distance
     with pytest.raises(L.MhbError):
         distance.haversine(0.0, 0.0, 1.0, 1.0)
+    # every other public module of the path: the same loud failure, never a numpy substitute
+    from pymhealth_b200 import fft, spectral
+    from pymhealth_b200.generic import timedom
+    from pymhealth_b200.heart import hrv, ppg
+    from pymhealth_b200.inertial import accelerometer as acc
+    from pymhealth_b200.location import features, distribution
+    from pymhealth_b200.util.windows import nonuniform_rolling_apply, get_indices
+    x = np.arange(64.0)
+    for call in (lambda: acc.magnitude(x, x, x), lambda: acc.rolling_magnitude(np.mean, 8, 4)(x, x, x),
+                 lambda: hrv.sdnn(x + 800.0), lambda: hrv.rmssd(x + 800.0), lambda: ppg.slope_sum(x, 5),
+                 lambda: timedom.gradient(x), lambda: timedom.zero_crossings(x), lambda: fft.fft(x),
+                 lambda: spectral.window_psd(x.astype(np.float32), 16, 8), lambda: get_indices(np.arange(64), 8, 4),
+                 lambda: nonuniform_rolling_apply(np.mean)(np.arange(64), x, 8, 4),
+                 lambda: features.arr_successive_distance(x, x), lambda: distribution.cluster_entropy(np.arange(8)),
+                 lambda: rolling_apply(spectral.spectral_entropy(50.0))(x.astype(np.float32), 16, 8)):
+        with pytest.raises(L.MhbError):
+            call()
 
 
 def test_unknown_reducers_are_rejected_not_run_on_cpu():
