@@ -24,6 +24,15 @@ def main():
     elif what.startswith("c4"):
         x = synth.device_ppg(32, 5_529_600, dev)
         W, S = 1920, 64
+    if what == "c3_mag":          # kernel 1a in magnitude mode: the three axis planes of the same tensor
+        nsub = x.shape[0] // 3
+        x3 = x.view(nsub, 3, -1)
+        out = torch.empty((nsub, engine.n_windows(x.shape[1], W, S), len(full)), dtype=torch.float32, device=dev)
+        for _ in range(iters):
+            engine.magnitude_window_table(x3[:, 0], x3[:, 1], x3[:, 2], W, S, full, out=out)
+        torch.cuda.synchronize()
+        print("ok", what, float(out[0, 0, 0]))
+        return
     feats = lvl0 if what.endswith("lvl0") else full
     if what.endswith("spec"):
         from pymhealth_b200 import spectral as SP
