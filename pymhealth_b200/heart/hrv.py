@@ -47,7 +47,6 @@ def nni_to_ms(nni, current_unit: str = 'ns'):
 
 
 def _diff_stats(nni, threshold=0.0):
-    import ctypes as C                                   # noqa: F401
     from ..engine import require_cuda, _stream_ptr
     torch = require_cuda()
     a = np.ascontiguousarray(np.asarray(nni, dtype=np.float64).ravel())

@@ -8,7 +8,6 @@ DataFrame forms are the same thin wrappers.  Result types follow numba's [probed
 return float64 degrees, integer input is promoted to float64.  The Butterworth ``linear_filter`` /
 ``gravity_filter`` of that module are scipy IIR recurrences and out of scope.
 """
-import ctypes as C
 from functools import singledispatch
 
 import numpy as np

@@ -2,7 +2,6 @@
 (reference src/mhealth/location/distance.py).  Degrees in, kilometres out, 2r = 12742.018,
 float64 throughout (the reference's gufuncs have float64-only signatures; float32 / integer
 inputs are promoted, as numpy does for them)."""
-import ctypes as C
 
 import numpy as np
 

@@ -2,7 +2,6 @@
 ``mhealth.location.distribution`` (reference src/mhealth/location/distribution.py:28-39, 58-102).
 ``cluster_locations`` (third-party HDBSCAN, distribution.py:42-55) is not ported: use
 ``location.features.stay_points`` for label assignment."""
-import ctypes as C
 
 import numpy as np
 

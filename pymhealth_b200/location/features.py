@@ -1,7 +1,6 @@
 """Location distance features -- drop-in for the array forms of ``mhealth.location.features``
 (reference src/mhealth/location/features.py:43-53, 71-84, 98-113).  The pandas DataFrame forms
 (features.py:11-40, 56-68, 87-95) are thin wrappers around them."""
-import ctypes as C
 
 import numpy as np
 

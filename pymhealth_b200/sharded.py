@@ -5,7 +5,6 @@ The hot path shards naturally -- windows never span series and day segments neve
 collective; the only exchange is one gather of the (small, fixed-width) feature tables, over NCCL on
 GPUs (NVLink 5 / NVSwitch) or gloo in the CPU tests.  One process per GPU, torch.distributed.
 """
-import numpy as np
 
 
 def bind_host_to_device_numa(device_index):
