@@ -48,6 +48,10 @@ template <typename T>
 struct Cx {
     T x, y;
 };
+template <>
+struct __align__(8) Cx<float> {      // a register pair: the operand of the packed FP32 instructions, one LDS.64 / STS.64
+    float x, y;
+};
 template <typename T>
 __device__ __forceinline__ Cx<T> cadd(Cx<T> a, Cx<T> b) { return {a.x + b.x, a.y + b.y}; }
 template <typename T>
@@ -58,6 +62,32 @@ template <typename T>
 __device__ __forceinline__ Cx<T> cscale(Cx<T> a, T s) { return {a.x * s, a.y * s}; }
 template <typename T>
 __device__ __forceinline__ Cx<T> mul_neg_i(Cx<T> a) { return {a.y, -a.x}; }   // a * (-i)
+// a + s b, a + (-i) b, a - (-i) b  (s real)
+template <typename T>
+__device__ __forceinline__ Cx<T> caxpy(T s, Cx<T> b, Cx<T> a) { return {a.x + s * b.x, a.y + s * b.y}; }
+template <typename T>
+__device__ __forceinline__ Cx<T> cadd_negi(Cx<T> a, Cx<T> b) { return {a.x + b.y, a.y - b.x}; }
+template <typename T>
+__device__ __forceinline__ Cx<T> csub_negi(Cx<T> a, Cx<T> b) { return {a.x - b.y, a.y + b.x}; }
+
+// ---- float32: Blackwell packed FP32 (crt/sm_100_rt.h: FADD2 / FMUL2 / FFMA2 on an aligned register pair).  A complex
+// value IS a pair, so every complex add is one instruction and a complex product two: the swapped / sign-flipped
+// operands these need (a.y, -a.x ...) are operand modifiers of the packed instructions (SASS `.F32x2.LO_HI.NP`), and a
+// real factor is a broadcast operand (`R.F32` or an immediate).  The FMA pipe retires a packed instruction in two
+// cycles, so the arithmetic throughput is that of the scalar form; what halves is the number of ISSUE SLOTS, which is
+// what bounds the FFT kernels (tools/ubench/packed_pipes.cu).
+__device__ __forceinline__ float2 f2(Cx<float> a) { return make_float2(a.x, a.y); }
+__device__ __forceinline__ Cx<float> cx(float2 a) { return {a.x, a.y}; }
+__device__ __forceinline__ Cx<float> cadd(Cx<float> a, Cx<float> b) { return cx(__fadd2_rn(f2(a), f2(b))); }
+__device__ __forceinline__ Cx<float> csub(Cx<float> a, Cx<float> b) { return cx(__fadd2_rn(f2(a), make_float2(-b.x, -b.y))); }
+__device__ __forceinline__ Cx<float> cmul(Cx<float> a, Cx<float> b) {
+    const float2 t = __fmul2_rn(make_float2(a.y, a.x), make_float2(-b.y, b.y));
+    return cx(__ffma2_rn(f2(a), make_float2(b.x, b.x), t));
+}
+__device__ __forceinline__ Cx<float> cscale(Cx<float> a, float s) { return cx(__fmul2_rn(f2(a), make_float2(s, s))); }
+__device__ __forceinline__ Cx<float> caxpy(float s, Cx<float> b, Cx<float> a) { return cx(__ffma2_rn(f2(b), make_float2(s, s), f2(a))); }
+__device__ __forceinline__ Cx<float> cadd_negi(Cx<float> a, Cx<float> b) { return cx(__fadd2_rn(f2(a), make_float2(b.y, -b.x))); }
+__device__ __forceinline__ Cx<float> csub_negi(Cx<float> a, Cx<float> b) { return cx(__fadd2_rn(f2(a), make_float2(-b.y, b.x))); }
 
 // fill tw[j] = exp(-2 pi i j / n), j = 0..count-1, cooperatively by `nthreads` threads
 template <typename T>
@@ -86,35 +116,35 @@ __device__ __forceinline__ void rdft2(Cf* a) {
 __device__ __forceinline__ void rdft3(Cf* a) {
     const float s = 0.86602540378443864676f;
     const Cf t1 = cadd(a[1], a[2]);
-    const Cf t2 = {a[0].x - 0.5f * t1.x, a[0].y - 0.5f * t1.y};
+    const Cf t2 = caxpy(-0.5f, t1, a[0]);
     const Cf t3 = cscale(csub(a[1], a[2]), s);
     a[0] = cadd(a[0], t1);
-    a[1] = {t2.x + t3.y, t2.y - t3.x};
-    a[2] = {t2.x - t3.y, t2.y + t3.x};
+    a[1] = cadd_negi(t2, t3);
+    a[2] = csub_negi(t2, t3);
 }
 __device__ __forceinline__ void rdft4(Cf* a) {
     const Cf t0 = cadd(a[0], a[2]), t1 = csub(a[0], a[2]);
-    const Cf t2 = cadd(a[1], a[3]), t3 = mul_neg_i(csub(a[1], a[3]));
+    const Cf t2 = cadd(a[1], a[3]), t3 = csub(a[1], a[3]);
     a[0] = cadd(t0, t2);
     a[2] = csub(t0, t2);
-    a[1] = cadd(t1, t3);
-    a[3] = csub(t1, t3);
+    a[1] = cadd_negi(t1, t3);
+    a[3] = csub_negi(t1, t3);
 }
-__device__ __forceinline__ void rdft5(Cf* a) {
+__device__ __forceinline__ void rdft5(Cf* a) {      // 18 packed instructions
     const float c1 = 0.30901699437494742410f, c2 = -0.80901699437494742410f;
     const float s1 = 0.95105651629515357212f, s2 = 0.58778525229247312917f;
     const Cf p1 = cadd(a[1], a[4]), m1 = csub(a[1], a[4]);
     const Cf p2 = cadd(a[2], a[3]), m2 = csub(a[2], a[3]);
     const Cf a0 = a[0];
-    a[0] = {a0.x + p1.x + p2.x, a0.y + p1.y + p2.y};
-    const Cf u1 = {fmaf(c2, p2.x, fmaf(c1, p1.x, a0.x)), fmaf(c2, p2.y, fmaf(c1, p1.y, a0.y))};
-    const Cf u2 = {fmaf(c1, p2.x, fmaf(c2, p1.x, a0.x)), fmaf(c1, p2.y, fmaf(c2, p1.y, a0.y))};
-    const Cf v1 = mul_neg_i(Cf{fmaf(s2, m2.x, s1 * m1.x), fmaf(s2, m2.y, s1 * m1.y)});
-    const Cf v2 = mul_neg_i(Cf{fmaf(-s1, m2.x, s2 * m1.x), fmaf(-s1, m2.y, s2 * m1.y)});
-    a[1] = cadd(u1, v1);
-    a[4] = csub(u1, v1);
-    a[2] = cadd(u2, v2);
-    a[3] = csub(u2, v2);
+    a[0] = cadd(cadd(a0, p1), p2);
+    const Cf u1 = caxpy(c2, p2, caxpy(c1, p1, a0));
+    const Cf u2 = caxpy(c1, p2, caxpy(c2, p1, a0));
+    const Cf t1 = caxpy(s2, m2, cscale(m1, s1));
+    const Cf t2 = caxpy(-s1, m2, cscale(m1, s2));
+    a[1] = cadd_negi(u1, t1);
+    a[4] = csub_negi(u1, t1);
+    a[2] = cadd_negi(u2, t2);
+    a[3] = csub_negi(u2, t2);
 }
 template <int R>
 __device__ __forceinline__ Cf rtw(int m);

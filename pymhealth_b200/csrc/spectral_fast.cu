@@ -65,28 +65,9 @@ struct FastPlan {
     int32_t use_tma;
 };
 
-// ---- small in-register DFTs (forward, e^{-2 pi i / R})
-__device__ __forceinline__ void dft2(C* a) {
-    const C t = a[1];
-    a[1] = csub(a[0], t);
-    a[0] = cadd(a[0], t);
-}
-__device__ __forceinline__ void dft5(C* a) {
-    const float c1 = 0.30901699437494742410f, c2 = -0.80901699437494742410f;
-    const float s1 = 0.95105651629515357212f, s2 = 0.58778525229247312917f;
-    const C p1 = cadd(a[1], a[4]), m1 = csub(a[1], a[4]);
-    const C p2 = cadd(a[2], a[3]), m2 = csub(a[2], a[3]);
-    const C a0 = a[0];
-    a[0] = {a0.x + p1.x + p2.x, a0.y + p1.y + p2.y};
-    const C u1 = {fmaf(c2, p2.x, fmaf(c1, p1.x, a0.x)), fmaf(c2, p2.y, fmaf(c1, p1.y, a0.y))};
-    const C u2 = {fmaf(c1, p2.x, fmaf(c2, p1.x, a0.x)), fmaf(c1, p2.y, fmaf(c2, p1.y, a0.y))};
-    const C v1 = mul_neg_i(C{fmaf(s2, m2.x, s1 * m1.x), fmaf(s2, m2.y, s1 * m1.y)});
-    const C v2 = mul_neg_i(C{fmaf(-s1, m2.x, s2 * m1.x), fmaf(-s1, m2.y, s2 * m1.y)});
-    a[1] = cadd(u1, v1);
-    a[4] = csub(u1, v1);
-    a[2] = cadd(u2, v2);
-    a[3] = csub(u2, v2);
-}
+// ---- small in-register DFTs (forward, e^{-2 pi i / R}): the packed butterflies of fft_core.cuh
+__device__ __forceinline__ void dft2(C* a) { rdft2(a); }
+__device__ __forceinline__ void dft5(C* a) { rdft5(a); }
 
 template <int R>
 __device__ __forceinline__ C ctw(int m);
@@ -311,6 +292,70 @@ __device__ __forceinline__ void reduce_rows(const FastPlan& P, const float* __re
     }
 }
 
+// ---- pass B of one (window, p): 10-point DFTs -> untangle -> |X|^2 -> PSD row + records.
+// Thread (w, p) transforms columns p and 25 - p of buf: A[k2] = Z[p + 25 k2] / 2, B[k2] = Z[25 - p + 25 k2] / 2, the
+// partner of bin k = p + 25 k2 being N - k = (25 - p) + 25 (9 - k2).  P0 (p = 0): the partner of 25 k2 is 25 (10 - k2), a
+// value of the SAME column, so one transform serves both sets; its k2 = 0 pair yields bins 0 and N, and the high-set
+// values k2 >= 1 duplicate the low set (they are kept out of the records).
+template <bool P0>
+__device__ __forceinline__ void pass_b(const C* __restrict__ bw, const C* __restrict__ twB, float* __restrict__ prow, int p,
+                                       int w, double* __restrict__ dcs, float pivot, const Records R) {
+    C A[10], B[10];
+#pragma unroll
+    for (int n2 = 0; n2 < 10; ++n2) {
+        A[n2] = bw[n2 * 25 + p];
+        if (!P0) B[n2] = bw[n2 * 25 + 25 - p];
+    }
+    dft10(A);
+    if (!P0) dft10(B);
+    float2 psd[10];                                // this thread's bins: .x low set (bin p + 25 k2), .y high set
+    float* lo_ptr = prow + p;                      // bin p + 25 k2
+    float* hi_ptr = prow + kN - p;                 // bin 250 - p - 25 k2
+#pragma unroll
+    for (int k2 = 0; k2 < 10; ++k2) {
+        const C zk = A[k2], zn = P0 ? A[(10 - k2) % 10] : B[9 - k2];       // (k, N - k), k = p + 25 k2
+        const C t2 = twB[k2 * kNP + p];
+        // e = zk + conj(zn), o = -i (zk - conj(zn)), X[k] = e + t2 o, conj(X[N - k]) = e - t2 o: eight packed
+        // instructions per pair of bins
+        const float2 e = __fadd2_rn(f2(zk), make_float2(zn.x, -zn.y));
+        const C o = cx(__fadd2_rn(make_float2(zk.y, -zk.x), make_float2(zn.y, zn.x)));
+        const C t = cmul(o, t2);
+        const float2 re = __fadd2_rn(make_float2(e.x, e.x), make_float2(t.x, -t.x));     // (Re X[k], Re X[N - k])
+        const float2 im = __fadd2_rn(make_float2(e.y, e.y), make_float2(t.y, -t.y));
+        psd[k2] = __ffma2_rn(re, re, __fmul2_rn(im, im));
+        if (!P0 || k2 == 0) hi_ptr[-25 * k2] = psd[k2].y;      // P0: bin N; the other high-set bins belong to the low set
+        if (!P0 || k2 > 0) lo_ptr[25 * k2] = psd[k2].x;
+    }
+    if (P0) {
+        // exact bin 0: FFT(x - m)[0] + W m in float64; the records must count every bin once
+        const double x0 = 2.0 * (static_cast<double>(A[0].x) + static_cast<double>(A[0].y)) +
+                          static_cast<double>(kW) * static_cast<double>(pivot);
+        dcs[w] = x0 * x0;
+        psd[0].x = 0.f;
+#pragma unroll
+        for (int k2 = 1; k2 < 10; ++k2) psd[k2].y = 0.f;
+    }
+    // records for the deferred reducers: total of the thread's bins, and the entropy partial in ONE pass: with
+    // y = psd 2^-e (e = binary exponent of this thread's total -- an exact scaling that keeps |log2 y| small for
+    // the bins that matter)  sum psd log2 psd = 2^e sum y log2 y + e tot
+    float2 tt = psd[0];
+#pragma unroll
+    for (int i = 1; i < 10; ++i) tt = __fadd2_rn(tt, psd[i]);
+    const float tot = tt.x + tt.y;
+    const int eb = (__float_as_int(tot) >> 23) & 0xff;
+    const float scale = __int_as_float((254 - eb) << 23);               // 2^-(eb - 127)
+    float2 hh = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int i = 0; i < 10; ++i) {
+        const float2 y = __fmul2_rn(psd[i], make_float2(scale, scale));
+        hh = __ffma2_rn(y, make_float2(__log2f(fmaxf(y.x, 1e-37f)), __log2f(fmaxf(y.y, 1e-37f))), hh);
+    }
+    const int q = w * kNP + p;
+    const_cast<float*>(R.ptot)[q] = tot;
+    const_cast<float*>(R.ph)[q] = hh.x + hh.y;
+    const_cast<int*>(R.pe)[q] = eb - 127;
+}
+
 #ifdef MHB_PHASE_TIMING
 #define MHB_TICK(ph)                                                             \
     do {                                                                         \
@@ -451,21 +496,23 @@ __global__ void __launch_bounds__(kThreadsF, 3) spectral_fast_kernel(const FastP
                 C a[25];
 #pragma unroll
                 for (int n1 = 0; n1 < 25; ++n1) {
-                    const float2 v = z[kNA * n1];
-                    a[n1] = {fmaf(v.x, 0.5f, mh), fmaf(v.y, 0.5f, mh)};
+                    a[n1] = cx(__ffma2_rn(z[kNA * n1], make_float2(0.5f, 0.5f), make_float2(mh, mh)));
                 }
                 dft25(a);
                 C* dst = buf + w * kWSB + n2 * 25;
                 dst[0] = a[0];
-                if (n2 == 0) {
+                // w250^(n2 k1); the n2 = 0 threads multiply by the table's exact (1, 0) (they share their warps with
+                // n2 = 1: a separate copy loop would only add a divergent path)
+                const C* tw = twA + n2;
 #pragma unroll
-                    for (int k1 = 1; k1 < 25; ++k1) dst[k1] = a[k1];
-                    piv[w] = m;
-                } else {
-                    const C* tw = twA + n2;
+                for (int k0 = 1; k0 < 25; k0 += 6) {       // six broadcast loads in flight, then their products
+                    C t[6];
 #pragma unroll
-                    for (int k1 = 1; k1 < 25; ++k1) dst[k1] = cmul(a[k1], tw[k1 * kNA]);
+                    for (int u = 0; u < 6; ++u) t[u] = tw[(k0 + u) * kNA];
+#pragma unroll
+                    for (int u = 0; u < 6; ++u) dst[k0 + u] = cmul(a[k0 + u], t[u]);
                 }
+                if (n2 == 0) piv[w] = m;
             }
         } else if (!first) {
             // ---- warps 5-7: PSD reducers of the PREVIOUS batch, whose rows sit in the other (consumed) tile slot
@@ -490,73 +537,9 @@ __global__ void __launch_bounds__(kThreadsF, 3) spectral_fast_kernel(const FastP
         // column 0 twice and rotates, B[m] = A[(m + 1) mod 10], because the partner of 25 k2 is 25 (10 - k2); its
         // k2 = 0 pair then yields bins 0 and N, and its high-set values k2 >= 1 are duplicates of its low set.
         if (role < kNP && act) {
-            const int p = role < kNP - 1 ? role + 1 : 0;   // p = 0 lives alone in the lower half of warp 6
-            const bool p0 = p == 0;
-            const C* bw = buf + w * kWSB;
             float* prow = tile + 2 * kBW + w * kRowStride;
-            C A[10], B[10];
-            const int pb = p0 ? 0 : 25 - p;
-#pragma unroll
-            for (int n2 = 0; n2 < 10; ++n2) {
-                A[n2] = bw[n2 * 25 + p];
-                B[n2] = bw[n2 * 25 + pb];
-            }
-            dft10(A);
-            dft10(B);
-            if (p0) {
-                const C b0 = B[0];
-#pragma unroll
-                for (int m = 0; m < 9; ++m) B[m] = B[m + 1];
-                B[9] = b0;
-            }
-            float psd[20];                                 // this thread's bins: [2 k2] low set, [2 k2 + 1] high set
-            float* lo_ptr = prow + p;                      // bin p + 25 k2
-            float* hi_ptr = prow + kN - p;                 // bin 250 - p - 25 k2
-#pragma unroll
-            for (int k2 = 0; k2 < 10; ++k2) {
-                const C zk = A[k2], zn = B[9 - k2];       // (k, N - k), k = p + 25 k2
-                const C t2 = twB[k2 * kNP + p];
-                const C e = {zk.x + zn.x, zk.y - zn.y};
-                const C o = {zk.y + zn.y, zn.x - zk.x};
-                const C t = cmul(o, t2);
-                const float ar = e.x + t.x, ai = e.y + t.y, br = e.x - t.x, bi2 = e.y - t.y;
-                psd[2 * k2] = fmaf(ar, ar, ai * ai);
-                psd[2 * k2 + 1] = fmaf(br, br, bi2 * bi2);
-                hi_ptr[-25 * k2] = psd[2 * k2 + 1];        // p = 0, k2 >= 1: rewritten below by the low-set twin
-                lo_ptr[25 * k2] = psd[2 * k2];             // p = 0, k2 = 0 lands in the unused cell prow[0]
-            }
-            if (p0) {
-                // exact bin 0: FFT(x - m)[0] + W m in float64; the records must count every bin once
-                const double x0 = 2.0 * (static_cast<double>(A[0].x) + static_cast<double>(A[0].y)) +
-                                  static_cast<double>(kW) * static_cast<double>(piv[w]);
-                reinterpret_cast<double*>(tile)[w] = x0 * x0;
-                psd[0] = 0.f;
-#pragma unroll
-                for (int k2 = 1; k2 < 10; ++k2) psd[2 * k2 + 1] = 0.f;
-            }
-            // records for the deferred reducers: total of the thread's bins, and the entropy partial in ONE pass: with
-            // y = psd 2^-e (e = binary exponent of this thread's total -- an exact scaling that keeps |log2 y| small for
-            // the bins that matter)  sum psd log2 psd = 2^e sum y log2 y + e tot
-            float ta = 0.f, tb = 0.f;
-#pragma unroll
-            for (int i = 0; i < 20; i += 2) {
-                ta += psd[i];
-                tb += psd[i + 1];
-            }
-            const float tot = ta + tb;
-            const int eb = (__float_as_int(tot) >> 23) & 0xff;
-            const float scale = __int_as_float((254 - eb) << 23);               // 2^-(eb - 127)
-            float ha = 0.f, hb = 0.f;
-#pragma unroll
-            for (int i = 0; i < 20; i += 2) {
-                const float y1 = psd[i] * scale, y2 = psd[i + 1] * scale;
-                ha = fmaf(y1, __log2f(fmaxf(y1, 1e-37f)), ha);
-                hb = fmaf(y2, __log2f(fmaxf(y2, 1e-37f)), hb);
-            }
-            const int q = w * kNP + p;
-            rec_tot[q] = tot;
-            rec_h[q] = ha + hb;
-            rec_e[q] = eb - 127;
+            if (role < kNP - 1) pass_b<false>(buf + w * kWSB, twB, prow, role + 1, w, nullptr, 0.f, R);
+            else pass_b<true>(buf + w * kWSB, twB, prow, 0, w, reinterpret_cast<double*>(tile), piv[w], R);   // p = 0 lives alone in the lower half of warp 6
         }
         MHB_TICK(3);                                       // pass B
         __syncthreads();                                   // (B2) PSD rows complete; buf free for the next pass A

@@ -214,7 +214,11 @@ def n_index_windows(first, last, wstep, is_float):
     if is_float:
         if not wstep > 0:
             raise ValueError("get_indices: wstep must be > 0")
-        return max(0, int(math.ceil((float(last) - float(first)) / float(wstep))))
+        delta = float(last) - float(first)
+        q = delta / float(wstep)
+        if q == 0.0 and delta != 0.0:          # numpy's underflow rule (PyArray_Arange): a denormal span still holds one key
+            return 0 if math.copysign(1.0, q) < 0 else 1
+        return max(0, int(math.ceil(q)))
     if int(wstep) <= 0:
         raise ValueError("get_indices: wstep must be > 0")
     return len(range(int(first), int(last), int(wstep)))
