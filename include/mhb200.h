@@ -167,6 +167,15 @@ int32_t mhb_segment_order_f64(const double* x, int64_t n, const int64_t* starts,
 int32_t mhb_window_spectral_f32(const float* x, const mhb_windows* geom, double fs,
                                 const int32_t* h_features, const double* h_params, int32_t n_features,
                                 const mhb_table* table, void* stream);
+/* Statistical and spectral columns of the SAME windows in one call -- what a caller of rolling_apply([np.mean, ...,
+ * band power, ...]) (util/windows.py:98-107: one full pass per reducer in the reference) wants.  stat_features are
+ * streaming-family ids (MHB_F_MEAN..MHB_F_SUM) written to stat_table, spec_features / spec_params as for
+ * mhb_window_spectral_f32 written to spec_table (the two tables may be column ranges of one array).  Kernel 1a and
+ * kernel 2 are launched back to back on `stream`. */
+int32_t mhb_window_features_f32(const float* x, const mhb_windows* geom, const int32_t* stat_features,
+                                int32_t n_stat, double zc_threshold, const mhb_table* stat_table, double fs,
+                                const int32_t* spec_features, const double* spec_params, int32_t n_spec,
+                                const mhb_table* spec_table, void* stream);
 /* Batched complex DFT of real or complex rows, replaces fftw_fft(n, in, out, dir)
  * (fft/_fftw_binder.py:11-17) / numpy.fft.fft: in = [n_rows][n] (real: float64; complex:
  * interleaved float64 pairs), out = [n_rows][n] interleaved complex128.  direction -1 forward
@@ -211,6 +220,11 @@ int32_t mhb_diff_stats_f64(const double* x, int64_t n, double abs_threshold, dou
  * timedom.zero_crossings(x, th) (:34-49) -> n - 1 flags, one byte each. */
 int32_t mhb_gradient(int32_t is_f64, const void* x, int64_t n, double* out, void* stream);
 int32_t mhb_zero_crossings(int32_t is_f64, const void* x, int64_t n, double threshold, uint8_t* out, void* stream);
+
+/* Raw int16 sensor counts -> float32 samples (out[i] = in[i] * scale, one rounding): the widening rolling_apply does
+ * per window on the host (util/windows.py:74-91 accepts any numeric dtype), done once on the device so that a host
+ * caller ships 2 bytes per sample. */
+int32_t mhb_widen_i16_f32(const int16_t* in, int64_t n, float scale, float* out, void* stream);
 
 /* ppg.slope_sum(x, w) (src/mhealth/heart/ppg.py:28-42): out[i] = sum(diff(x)[i-w : i]) for w <= i < n - 1, else 0;
  * float64 [n] out whatever the input type. */

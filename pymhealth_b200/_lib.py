@@ -72,6 +72,9 @@ SIGNATURES = {
                                           C.c_int32, C.POINTER(MhbTable), _vp]),
     "mhb_window_spectral_f32": (C.c_int32, [_vp, C.POINTER(MhbWindows), C.c_double, _i32p, _f64p, C.c_int32,
                                             C.POINTER(MhbTable), _vp]),
+    "mhb_window_features_f32": (C.c_int32, [_vp, C.POINTER(MhbWindows), _i32p, C.c_int32, C.c_double, C.POINTER(MhbTable),
+                                            C.c_double, _i32p, _f64p, C.c_int32, C.POINTER(MhbTable), _vp]),
+    "mhb_widen_i16_f32": (C.c_int32, [_vp, C.c_int64, C.c_float, _vp, _vp]),
     "mhb_psd_reduce_f64": (C.c_int32, [_vp, _vp, C.c_int64, C.c_int32, _i32p, _f64p, C.c_int32, _vp, _vp]),
     "mhb_fft_c128": (C.c_int32, [_vp, C.c_int32, C.c_int64, C.c_int32, C.c_int32, _vp, _vp]),
     "mhb_window_psd_f32": (C.c_int32, [_vp, C.POINTER(MhbWindows), _vp, C.c_int32, _vp]),

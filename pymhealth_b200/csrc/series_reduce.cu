@@ -201,3 +201,47 @@ extern "C" int32_t mhb_diff_stats_f64(const double* x, int64_t n, double abs_thr
     diff_final_kernel<<<1, 32, 0, s>>>(x, n - 1, part, blocks, out7);
     return cuda_status(cudaGetLastError(), "diff_stats launch");
 }
+
+// ---------------------------------------------------------------------------------------------
+// Raw sensor counts -> float32 samples on the device.  rolling_apply takes any numeric dtype (util/windows.py:74-91
+// casts the window to the reducer's input type); wearable loggers store int16 counts, so a host-side caller ships
+// 2 bytes per sample over PCIe and widens here (exact: |count| < 2^15, and `scale` is applied as one rounded
+// multiplication, e.g. 1 / 4096 g per count).  HBM-bound: 8 counts per thread through one 128-bit load.
+namespace mhb {
+namespace {
+__global__ void __launch_bounds__(256) widen_i16_kernel(const int16_t* __restrict__ in, int64_t n, float scale,
+                                                         float* __restrict__ out) {
+    const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+    const int64_t n8 = ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) % 16 == 0) ? n / 8 : 0;
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n8; i += stride) {
+        const int4 q = reinterpret_cast<const int4*>(in)[i];
+        const int v[4] = {q.x, q.y, q.z, q.w};
+        float4 a, b;
+        a.x = static_cast<float>(static_cast<short>(v[0] & 0xffff)) * scale;
+        a.y = static_cast<float>(v[0] >> 16) * scale;
+        a.z = static_cast<float>(static_cast<short>(v[1] & 0xffff)) * scale;
+        a.w = static_cast<float>(v[1] >> 16) * scale;
+        b.x = static_cast<float>(static_cast<short>(v[2] & 0xffff)) * scale;
+        b.y = static_cast<float>(v[2] >> 16) * scale;
+        b.z = static_cast<float>(static_cast<short>(v[3] & 0xffff)) * scale;
+        b.w = static_cast<float>(v[3] >> 16) * scale;
+        reinterpret_cast<float4*>(out)[2 * i] = a;
+        reinterpret_cast<float4*>(out)[2 * i + 1] = b;
+    }
+    for (int64_t i = n8 * 8 + static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride)
+        out[i] = static_cast<float>(in[i]) * scale;
+}
+}  // namespace
+}  // namespace mhb
+
+extern "C" int32_t mhb_widen_i16_f32(const int16_t* in, int64_t n, float scale, float* out, void* stream) {
+    using namespace mhb;
+    MHB_REQUIRE(n >= 0, MHB_E_ARG, "widen_i16: negative size");
+    if (n == 0) return MHB_OK;
+    MHB_REQUIRE(in && out, MHB_E_ARG, "widen_i16: null pointer");
+    int64_t blocks = (n / 8 + 255) / 256 + 1;
+    const int64_t cap = static_cast<int64_t>(kNumSMs) * 16;
+    if (blocks > cap) blocks = cap;
+    widen_i16_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(in, n, scale, out);
+    return cuda_status(cudaGetLastError(), "widen_i16 launch");
+}

@@ -536,10 +536,15 @@ __global__ void __launch_bounds__(kThreadsF, 3) spectral_fast_kernel(const FastP
         // the partner of bin k = p + 25 k2 being N - k = (25 - p) + 25 (9 - k2).  p = 0 runs the SAME code: it loads
         // column 0 twice and rotates, B[m] = A[(m + 1) mod 10], because the partner of 25 k2 is 25 (10 - k2); its
         // k2 = 0 pair then yields bins 0 and N, and its high-set values k2 >= 1 are duplicates of its low set.
-        if (role < kNP && act) {
+        // Pass-B roles are handed out from the LAST half-warp down (role_b = 15 - role): pass A keeps warps 0-4 busy, i.e.
+        // two warps of sub-partition 0 (warp w runs on sub-partition w mod 4) and one of each other; counting from the
+        // top gives sub-partition 0 one pass-B warp (warp 4) and the others two, so the FMA-pipe cycles of a batch are
+        // spread 1830 / 1480 / 1710 / 1710 over the four schedulers instead of 2360 / 1710 / 1710 / 1180.
+        const int role_b = 15 - role;
+        if (role_b < kNP && act) {
             float* prow = tile + 2 * kBW + w * kRowStride;
-            if (role < kNP - 1) pass_b<false>(buf + w * kWSB, twB, prow, role + 1, w, nullptr, 0.f, R);
-            else pass_b<true>(buf + w * kWSB, twB, prow, 0, w, reinterpret_cast<double*>(tile), piv[w], R);   // p = 0 lives alone in the lower half of warp 6
+            if (role_b < kNP - 1) pass_b<false>(buf + w * kWSB, twB, prow, role_b + 1, w, nullptr, 0.f, R);
+            else pass_b<true>(buf + w * kWSB, twB, prow, 0, w, reinterpret_cast<double*>(tile), piv[w], R);   // p = 0: upper half of warp 1
         }
         MHB_TICK(3);                                       // pass B
         __syncthreads();                                   // (B2) PSD rows complete; buf free for the next pass A

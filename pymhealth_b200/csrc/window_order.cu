@@ -97,6 +97,7 @@ __device__ __forceinline__ double percentile_sorted(const InT* s, int n, double 
     const double f = floor(rank);
     const double m = rank - f;
     const int fi = static_cast<int>(f);
+    if (fi >= n) return static_cast<double>(s[n - 1]);      // q just below 100: the rank rounds to n (m = 0); never read s[n]
     const double lower = static_cast<double>(s[fi - 1]);
     const double upper = static_cast<double>(s[fi]);
     return lower * (1 - m) + upper * m;

@@ -286,7 +286,8 @@ __global__ void get_indices_kernel(const T* __restrict__ index, int64_t n, T fir
     const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i >= 2 * nwin) return;
     const int64_t wi = i < nwin ? i : i - nwin;
-    // np.arange(start, stop, step)[i] = start + i * step (exact for integers; numpy's float fill is the same form)
+    // np.arange(start, stop, step)[i] = start + i * delta: exact for integers; for floats numpy fills with
+    // delta = (start + step) - start in float64, which the host passes as `wstep` (engine.device_get_indices)
     T key = first + static_cast<T>(wi) * wstep;
     if (i >= nwin) key = key + wsize;
     int64_t lo = 0, hi = n;                  // first position with index[pos] >= key  (side='left')

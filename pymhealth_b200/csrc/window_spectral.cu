@@ -520,6 +520,24 @@ extern "C" int32_t mhb_window_spectral_f32(const float* x, const mhb_windows* ge
                                 "window_spectral");
 }
 
+// Statistical (kernel 1a family) and spectral columns of the same windows in ONE call: kernel 1a and kernel 2 launched back
+// to back on the caller's stream (see DESIGN.md section 4 for why the two are not one kernel: both are bound by
+// instruction issue / latency, not by HBM, and the fused, warp-specialised variant measured 2x slower).
+extern "C" int32_t mhb_window_features_f32(const float* x, const mhb_windows* geom, const int32_t* stat_features,
+                                           int32_t n_stat, double zc_threshold, const mhb_table* stat_table, double fs,
+                                           const int32_t* spec_features, const double* spec_params, int32_t n_spec,
+                                           const mhb_table* spec_table, void* stream) {
+    MHB_REQUIRE(n_stat >= 0 && n_spec >= 0, MHB_E_ARG, "window_features: negative column count");
+    MHB_REQUIRE(n_stat == 0 || (stat_features && stat_table), MHB_E_ARG, "window_features: null statistics list / table");
+    MHB_REQUIRE(n_spec == 0 || (spec_features && spec_table), MHB_E_ARG, "window_features: null spectral list / table");
+    if (n_stat > 0) {
+        const int32_t st = mhb_window_stats_f32(x, geom, stat_features, n_stat, zc_threshold, stat_table, stream);
+        if (st != MHB_OK) return st;
+    }
+    if (n_spec > 0) return mhb_window_spectral_f32(x, geom, fs, spec_features, spec_params, n_spec, spec_table, stream);
+    return MHB_OK;
+}
+
 extern "C" int32_t mhb_window_psd_f32(const float* x, const mhb_windows* geom, void* psd_out, int32_t out_f32,
                                       void* stream) {
     MHB_REQUIRE(geom, MHB_E_ARG, "window_psd: null geometry");

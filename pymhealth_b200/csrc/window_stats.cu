@@ -37,7 +37,7 @@ namespace {
 constexpr int kThreads = 256;
 constexpr int kMaxFeat = 32;
 constexpr int kDirectK = 8;      // windows of <= kDirectK blocks are summed directly
-constexpr int kNPre = 6;         // S1..S4, LL, ZC get a running prefix when k > kDirectK
+constexpr int kNPre = 7;         // S1..S4, LL, ZC get a running prefix when k > kDirectK; the 7th counts non-finite blocks
 
 struct StatsPlan {
     const void* x;
@@ -100,18 +100,27 @@ static size_t partial_bytes(size_t in_size, bool m4, bool td, int n) {
     return ((b + 15) & ~size_t(15)) + 16;
 }
 
+// min / max that PROPAGATE NaN, as np.min / np.max do (fminf / fmaxf would silently drop it): FMNMX.NAN for float32
 template <typename T>
 __device__ __forceinline__ T tmin(T a, T b);
 template <>
-__device__ __forceinline__ float tmin<float>(float a, float b) { return fminf(a, b); }
+__device__ __forceinline__ float tmin<float>(float a, float b) {
+    float r;
+    asm("min.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
+    return r;
+}
 template <>
-__device__ __forceinline__ double tmin<double>(double a, double b) { return fmin(a, b); }
+__device__ __forceinline__ double tmin<double>(double a, double b) { return (a != a || b != b) ? a + b : fmin(a, b); }
 template <typename T>
 __device__ __forceinline__ T tmax(T a, T b);
 template <>
-__device__ __forceinline__ float tmax<float>(float a, float b) { return fmaxf(a, b); }
+__device__ __forceinline__ float tmax<float>(float a, float b) {
+    float r;
+    asm("max.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
+    return r;
+}
 template <>
-__device__ __forceinline__ double tmax<double>(double a, double b) { return fmax(a, b); }
+__device__ __forceinline__ double tmax<double>(double a, double b) { return (a != a || b != b) ? a + b : fmax(a, b); }
 
 template <typename InT>
 struct CellAcc {
@@ -342,7 +351,10 @@ __global__ void __launch_bounds__(kThreads, 3) window_stats_kernel(const StatsPl
             __syncthreads();
         }
         const InT* s = buf + d.lead;
-        if (st == 0) c = static_cast<double>(ld(s, 0));
+        if (st == 0) {
+            c = static_cast<double>(ld(s, 0));
+            if (!isfinite(c)) c = 0.0;      // a NaN / inf first sample must not poison the whole chunk (any pivot is exact)
+        }
 
         // ---------------- phase 1: one cell per thread
         const int ncell = d.nblk * g_cpb;
@@ -492,13 +504,17 @@ __global__ void __launch_bounds__(kThreads, 3) window_stats_kernel(const StatsPl
         if (use_prefix) {
             const int warp = tid >> 5, lane = tid & 31;
             constexpr int nq = 2 + (M4 ? 2 : 0) + (TD ? 2 : 0);
-            if (warp < nq) {                        // one warp per additive quantity
-                // quantity order: s1, s2, [s3, s4], [ll, zc]
+            if (warp <= nq) {                       // one warp per additive quantity + one for the non-finite count
+                // quantity order: s1, s2, [s3, s4], [ll, zc]; q == nq: number of blocks whose partials are not finite.
+                // Such a block enters the prefixes as ZERO (a NaN there would poison every later window of the chunk
+                // through pre[hi] - pre[lo]); windows that cover one are summed directly in phase 3 instead.
                 const int q = warp;
-                const bool is_f = TD && q >= nq - 2;
+                const bool is_cnt = q == nq;
+                const bool is_f = TD && q >= nq - 2 && !is_cnt;
                 const double* srcd = q == 0 ? ring.s1 : q == 1 ? ring.s2 : (M4 && q == 2) ? ring.s3 : ring.s4;
                 const float* srcf = (q == nq - 2) ? ring.ll : ring.zc;
-                double run = carry[q];
+                const int qs = is_cnt ? kNPre - 1 : q;                            // prefix / carry slot
+                double run = carry[qs];
                 int pslot = pre_emit + (blocks_done - emitted * g_hop);          // prefix slot of block blocks_done
                 while (pslot >= R1) pslot -= R1;                                  // (no integer division in the stage loop)
                 while (pslot < 0) pslot += R1;
@@ -507,17 +523,21 @@ __global__ void __launch_bounds__(kThreads, 3) window_stats_kernel(const StatsPl
                     double v = 0.0;
                     if (b < d.nblk) {
                         const int r = wrap(ring_head + b, P.RB);
-                        v = is_f ? static_cast<double>(srcf[r]) : srcd[r];
+                        bool bad = !isfinite(ring.s1[r]) || !isfinite(ring.s2[r]);
+                        if (M4) bad = bad || !isfinite(ring.s3[r]) || !isfinite(ring.s4[r]);
+                        if (TD) bad = bad || !isfinite(ring.ll[r]);
+                        if (is_cnt) v = bad ? 1.0 : 0.0;
+                        else if (!bad) v = is_f ? static_cast<double>(srcf[r]) : srcd[r];
                     }
 #pragma unroll
                     for (int o = 1; o < 32; o <<= 1) {
                         const double u = __shfl_up_sync(0xffffffffu, v, o);
                         if (lane >= o) v += u;
                     }
-                    if (b < d.nblk) pre[q * R1 + wrap(pslot + b + 1, R1)] = run + v;
+                    if (b < d.nblk) pre[qs * R1 + wrap(pslot + b + 1, R1)] = run + v;
                     run += __shfl_sync(0xffffffffu, v, 31);
                 }
-                if (lane == 0) carry[q] = run;
+                if (lane == 0) carry[qs] = run;
             }
             __syncthreads();
         }
@@ -539,7 +559,15 @@ __global__ void __launch_bounds__(kThreads, 3) window_stats_kernel(const StatsPl
                 double S1, S2, S3 = 0, S4 = 0, LL = 0, ZC = 0;
                 InT mn = ring.mn[r0], mx = ring.mx[r0];
                 int r = r0;
-                if (!use_prefix) {
+                bool direct = !use_prefix;
+                int lo = 0, hi = 0;
+                if (use_prefix) {
+                    lo = wrap(pre_emit + rel, R1);
+                    hi = lo + g_k;
+                    while (hi >= R1) hi -= R1;
+                    direct = pre[(kNPre - 1) * R1 + hi] != pre[(kNPre - 1) * R1 + lo];      // a non-finite block inside
+                }
+                if (direct) {
                     S1 = ring.s1[r0];
                     S2 = ring.s2[r0];
                     if (M4) {
@@ -566,9 +594,6 @@ __global__ void __launch_bounds__(kThreads, 3) window_stats_kernel(const StatsPl
                         mx = tmax<InT>(mx, ring.mx[r]);
                     }
                 } else {
-                    const int lo = wrap(pre_emit + rel, R1);
-                    int hi = lo + g_k;
-                    while (hi >= R1) hi -= R1;
                     S1 = pre[0 * R1 + hi] - pre[0 * R1 + lo];
                     S2 = pre[1 * R1 + hi] - pre[1 * R1 + lo];
                     if (M4) {

@@ -112,6 +112,7 @@ def window_table(x, wsize, wstep, features, zc_threshold=0.0, fs=1.0, out_dtype=
         out = torch.empty((ns, nw, nf), dtype=out_dtype, device=t.device)
     elif tuple(out.shape) != (ns, nw, nf):
         raise ValueError("out has shape %s, expected %s" % (tuple(out.shape), (ns, nw, nf)))
+    _check_out(torch, out, t)
     if nw > 0 and ns > 0 and nf > 0:
         geom = L.MhbWindows(ns, n, t.stride(0) if ns > 1 else n, wsize, wstep)
         stream = _stream_ptr(torch)
@@ -119,12 +120,31 @@ def window_table(x, wsize, wstep, features, zc_threshold=0.0, fs=1.0, out_dtype=
         by_family = {"stream": [], "order": [], "spectral": []}
         for j, f in enumerate(features):
             by_family[f.family].append(j)
+        # statistical + spectral columns of the same float32 windows: ONE C-ABI call (kernel 1a and kernel 2 back to
+        # back on the stream); the order family follows on its own
+        s_runs, p_runs = _runs(by_family["stream"]), _runs(by_family["spectral"])
+        if f32_in and len(s_runs) == 1 and len(p_runs) == 1:
+            sr, pr = s_runs[0], p_runs[0]
+            esz = out.stride(2) * out.element_size()
+            f32o = 1 if out.dtype == torch.float32 else 0
+            stab = L.MhbTable(out.data_ptr() + sr[0] * esz, f32o, out.stride(0), out.stride(1), out.stride(2))
+            ptab = L.MhbTable(out.data_ptr() + pr[0] * esz, f32o, out.stride(0), out.stride(1), out.stride(2))
+            flat = []
+            for j in pr:
+                p = features[j].params
+                flat += [p[0] if len(p) > 0 else math.nan, p[1] if len(p) > 1 else math.nan]
+            st = lib.mhb_window_features_f32(t.data_ptr(), C.byref(geom), L.i32_array([features[j].fid for j in sr]), len(sr),
+                                             float(zc_threshold), C.byref(stab), float(fs),
+                                             L.i32_array([features[j].fid for j in pr]), L.f64_array(flat), len(pr),
+                                             C.byref(ptab), stream)
+            L.check(st, "window_features")
+            by_family = {"order": by_family["order"]}
         # columns of one family must be contiguous-strided for the table descriptor: launch each
         # family on maximal runs of consecutive columns
         for family, cols in by_family.items():
             for run in _runs(cols):
                 j0 = run[0]
-                tab = L.MhbTable(out.data_ptr() + j0 * out.element_size(), 1 if out.dtype == torch.float32 else 0,
+                tab = L.MhbTable(out.data_ptr() + j0 * out.stride(2) * out.element_size(), 1 if out.dtype == torch.float32 else 0,
                                  out.stride(0), out.stride(1), out.stride(2))
                 ids = L.i32_array([features[j].fid for j in run])
                 if family == "stream":
@@ -148,6 +168,14 @@ def window_table(x, wsize, wstep, features, zc_threshold=0.0, fs=1.0, out_dtype=
         res = out.cpu().numpy()
         return res[0] if was_1d else res
     return out[0] if was_1d else out
+
+
+def _check_out(torch, out, t):
+    """A caller-supplied table must be float32 / float64 on the input's device (any element strides are fine)."""
+    if out.dtype not in (torch.float32, torch.float64):
+        raise TypeError("out must be float32 or float64, not %s" % out.dtype)
+    if out.device != t.device:
+        raise ValueError("out is on %s, the series on %s" % (out.device, t.device))
 
 
 def magnitude_window_table(x, y, z, wsize, wstep, features, zc_threshold=0.0, fs=1.0, out_dtype=None, out=None):
@@ -182,6 +210,7 @@ def magnitude_window_table(x, y, z, wsize, wstep, features, zc_threshold=0.0, fs
         out = torch.empty((ns, nw, nf), dtype=out_dtype, device=tx.device)
     elif tuple(out.shape) != (ns, nw, nf):
         raise ValueError("out has shape %s, expected %s" % (tuple(out.shape), (ns, nw, nf)))
+    _check_out(torch, out, tx)
     if nw > 0 and ns > 0 and nf > 0:
         stream = _stream_ptr(torch)
         s_cols = [j for j, f in enumerate(features) if f.family == "stream"]
@@ -189,7 +218,7 @@ def magnitude_window_table(x, y, z, wsize, wstep, features, zc_threshold=0.0, fs
         geom = L.MhbWindows(ns, n, row_stride, wsize, wstep)
         fn = lib.mhb_window_stats_magnitude_f32 if dt == torch.float32 else lib.mhb_window_stats_magnitude_f64
         for run in _runs(s_cols):
-            tab = L.MhbTable(out.data_ptr() + run[0] * out.element_size(), 1 if out.dtype == torch.float32 else 0,
+            tab = L.MhbTable(out.data_ptr() + run[0] * out.stride(2) * out.element_size(), 1 if out.dtype == torch.float32 else 0,
                              out.stride(0), out.stride(1), out.stride(2))
             ids = L.i32_array([features[j].fid for j in run])
             L.check(fn(tx.data_ptr(), ty.data_ptr(), tz.data_ptr(), C.byref(geom), ids, len(run), float(zc_threshold),
@@ -270,7 +299,10 @@ def device_get_indices(index, wsize, wstep):
     out = torch.empty((2, nwin), dtype=torch.int64, device=it.device)
     if nwin:
         fn = lib.mhb_get_indices_f64 if is_f else lib.mhb_get_indices_i64
-        st = fn(it.data_ptr(), n, first, wsize, wstep, nwin, out.data_ptr(), _stream_ptr(torch))
+        # numpy fills a float arange as start + i * delta with delta = (start + step) - start, not always the same
+        # double as step (start = 0.1, step = 0.2 -> 0.20000000000000004): keys on window boundaries depend on it
+        kstep = (first + wstep) - first if is_f else wstep
+        st = fn(it.data_ptr(), n, first, wsize, kstep, nwin, out.data_ptr(), _stream_ptr(torch))
         L.check(st, "get_indices")
     return out
 
@@ -316,7 +348,7 @@ def segment_table(x, indices, features, min_window_len=1, zc_threshold=0.0, out_
     for family, cols in by_family.items():
         for run in _runs(cols):
             j0 = run[0]
-            tab = L.MhbTable(out.data_ptr() + j0 * out.element_size(), 1 if out.dtype == torch.float32 else 0,
+            tab = L.MhbTable(out.data_ptr() + j0 * out.stride(1) * out.element_size(), 1 if out.dtype == torch.float32 else 0,
                              0, out.stride(0), out.stride(1))
             ids = L.i32_array([features[j].fid for j in run])
             if family == "stream":

@@ -54,3 +54,22 @@ def test_no_cuda_means_an_error_not_a_fallback():
     from pymhealth_b200.util import rolling_apply
     with pytest.raises(_lib.MhbError):
         rolling_apply(np.mean)(np.arange(100.0), 10, 5)
+
+
+def test_product_view_is_the_reference_view(ref_windows):
+    """pymhealth_b200.util.windows.view (util/windows.py:20-33 of the reference): same shape, same values, zero-copy --
+    against the reference-generated fixture and the strided definition, for 1-D float / int input."""
+    from pymhealth_b200.util.windows import view
+    from oracle import windows as OW
+    xv = ref_windows["view/x"]
+    got = view(xv, 5, 3)
+    np.testing.assert_array_equal(got, ref_windows["view/5_3"])
+    assert np.shares_memory(got, xv) and got.dtype == xv.dtype
+    rng = np.random.default_rng(5)
+    for n, w, s in [(10, 3, 1), (10, 10, 4), (6137, 500, 250), (100, 7, 13), (64, 64, 1)]:
+        for x in (rng.standard_normal(n), rng.integers(-9, 9, n).astype(np.int16)):
+            v = view(x, w, s)
+            assert v.shape == (1 + (n - w) // s, w)
+            np.testing.assert_array_equal(v, OW.view(x, w, s))
+            for i in (0, v.shape[0] - 1):
+                np.testing.assert_array_equal(v[i], x[i * s:i * s + w])

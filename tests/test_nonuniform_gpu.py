@@ -111,3 +111,17 @@ def test_long_windows():
     for g, name in zip(got, ["mean", "var", "min", "max"]):
         want = OW.nonuniform_rolling(name, idx, x, 86400, 43200)
         np.testing.assert_allclose(g, want, rtol=1e-10, err_msg=name)
+
+
+def test_get_indices_float_keys_on_window_boundaries():
+    """Regularly sampled FLOAT timestamps put index values exactly on window boundaries, where the left searchsorted
+    depends on the last bit of every key: numpy fills arange(start, stop, step) as start + i * delta with
+    delta = (start + step) - start (float64), which is not always the double `step` (0.1, 0.2 -> 0.20000000000000004)."""
+    from oracle import windows as OW
+    from pymhealth_b200.util.windows import get_indices
+    for start, dt, wsize, wstep in [(0.1, 0.1, 0.6, 0.2), (0.1, 0.05, 1.0, 0.2), (1e6 + 0.3, 0.1, 0.7, 0.3), (0.0, 0.25, 2.0, 0.5),
+                                    (17.7, 0.02, 0.3, 0.06)]:
+        idx = start + dt * np.arange(20_000)
+        want = OW.get_indices(idx, wsize, wstep)
+        got = get_indices(idx, wsize, wstep)
+        np.testing.assert_array_equal(got, want, err_msg=str((start, dt, wsize, wstep)))

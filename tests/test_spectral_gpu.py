@@ -225,3 +225,30 @@ def test_linearity_and_parseval_full_config2():
     psd2, _ = SP.window_psd(x * 3.0, W, S, 50.0, out_dtype=torch.float64)
     err = (psd2 - psd * 9.0).abs().amax(dim=-1)
     assert bool((err <= 1e-5 * 9.0 * psd.amax(dim=-1)).all())      # float32 FFT: error scales with the row's peak
+
+
+def test_hrv_peak_frequency_intent():
+    """heart.hrv.peak_frequency: the reference (heart/hrv.py:182-189) returns freqs[argmax(psd[mask])] -- the UNMASKED
+    frequency vector indexed with the masked arg-max, correct only while the mask starts at bin 0.  The drop-in
+    implements the evident intent, freqs[mask][argmax(psd[mask])] (both bounds inclusive, first maximum), and agrees
+    with the reference's own expression wherever that expression is right (lower = None / lower <= min f)."""
+    from pymhealth_b200.heart import hrv
+    rng = np.random.default_rng(11)
+    freqs = np.fft.rfftfreq(500, 1 / 50.0)
+    for trial in range(12):
+        psd = rng.gamma(2.0, 1.0, freqs.size)
+        psd[rng.integers(0, freqs.size)] += 25.0                       # a clear peak somewhere
+        for lower, upper in [(None, None), (None, 7.5), (0.0, 12.0), (0.3, 12.0), (3.0, 8.0), (8.0, 8.0), (2.05, 2.35)]:
+            lo = freqs.min() if lower is None else lower
+            hi = freqs.max() if upper is None else upper
+            mask = np.logical_and(freqs >= lo, freqs <= hi)
+            if not mask.any():
+                continue
+            want = freqs[mask][np.argmax(psd[mask])]
+            got = hrv.peak_frequency(psd, freqs, lower, upper)
+            assert got == want, (trial, lower, upper, got, want)
+            if lo <= freqs.min():                                      # where the reference's formula is correct
+                assert got == freqs[np.argmax(psd[mask])]
+    # ties: the first maximum wins, as np.argmax does
+    psd = np.ones(freqs.size)
+    assert hrv.peak_frequency(psd, freqs, 1.0, 2.0) == freqs[np.nonzero(freqs >= 1.0)[0][0]]

@@ -77,3 +77,18 @@ def test_direct_calls_and_mixed_families(ref_windows):
         np.testing.assert_allclose(g, ref_windows["acc_z_500_250/" + k], rtol=1e-9)
     with pytest.raises(ValueError):
         rolling_apply(functools.partial(np.percentile, q=101))(x, 500, 250)
+
+
+@pytest.mark.parametrize("W,S", [(64, 16), (256, 256), (500, 250), (33, 7)])
+def test_percentile_next_to_100(W, S):
+    """q one ulp below 100: numba's rank 1 + (n - 1) q / 100 rounds to n, i.e. the largest element with weight 1 --
+    never a read past the window.  Also q next to 0."""
+    from pymhealth_b200.util import rolling_apply
+    rng = np.random.default_rng(W)
+    x = rng.standard_normal(4000).astype(np.float32)
+    qhi, qlo = float(np.nextafter(100.0, 0.0)), float(np.nextafter(0.0, 1.0))
+    hi, lo, mx, mn = rolling_apply([functools.partial(np.percentile, q=qhi), functools.partial(np.percentile, q=qlo),
+                                    np.max, np.min])(x, W, S)
+    assert np.all(np.isfinite(hi)) and np.all(np.isfinite(lo))
+    np.testing.assert_allclose(hi, mx, rtol=1e-12)
+    np.testing.assert_allclose(lo, mn, rtol=1e-12, atol=1e-300)
