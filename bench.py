@@ -2,13 +2,19 @@
 """Benchmark of the window-feature hot path (BASELINE.json: "feature windows/sec at 1/2/4/8 B200 +
 HBM GB/s fraction vs numba host").
 
-Workload = BASELINE.json configs[2] (1,000 subjects x 7 days triaxial accelerometer at 50 Hz, 10 s
+Headline workload = BASELINE.json configs[2] (1,000 subjects x 7 days triaxial accelerometer at 50 Hz, 10 s
 windows with 50 % overlap, sharded by subject), weak scaling: every GPU holds 125 subjects (45.4 GB of
 float32 samples resident in HBM), so 8 GPUs process exactly the 1,000-subject configuration and N GPUs
-process 125 N subjects.  A step is one pass of the hot path over the rank's shard: kernel 1a (10
-statistical / time-domain columns) + kernel 2 (FFT + 6 spectral columns) -> one [windows, 16] float32
-feature table.  No collective is on the data path (subjects are independent); the only NCCL traffic is the
-gather of a per-subject summary table after the timed region.
+process 125 N subjects.  A step is one pass of the hot path over the rank's shard: ONE call of
+mhb_window_features_f32 (kernel 1a: 10 statistical / time-domain columns + kernel 2: FFT + 6 spectral columns)
+-> one [windows, 16] float32 feature table; `value_with_order` adds kernel 1b (median + 90th percentile) to the
+step.  No collective is on the data path (subjects are independent).
+
+The same JSON line carries the other BASELINE configurations, each timed the same way (device-resident, CUDA
+events, max over ranks): `config4_ppg` (configs[3]: 500 subjects x 24 h PPG at 64 Hz, W = 1920 / S = 64, split
+over the ranks), `config5_gps` (configs[4]: 10,000 subjects x 30 d GPS at 1 Hz, 1,250 subjects per GPU, per-day
+feature rows + the NCCL gather of the [subject-days, 11] tables INSIDE the timed region) and `config1_gps`
+(configs[0]: one 7-day trace through the drop-in location functions, host arrays in and out).
 
     python bench.py --gpus 1 --steps 10 --warmup 3
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
@@ -53,16 +59,26 @@ def feature_list():
     return stream, spec
 
 
+def lib_sha256():
+    import hashlib
+    p = os.path.join(ROOT, "pymhealth_b200", "libmhb200.so")
+    try:
+        return hashlib.sha256(open(p, "rb").read()).hexdigest()
+    except Exception:
+        return None
+
+
 def ncu_traffic(nsub):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures of the bench
-    launches (profiles/ncu_traffic.json, written by tools/ncu_traffic.py from the .ncu-rep files); {} when absent or
-    taken at another shard size."""
+    launches (profiles/ncu_traffic.json, written by tools/ncu_traffic.py from the .ncu-rep files).  The file names the
+    sha256 of the libmhb200.so it was taken from and the shard size: a capture of another build or another size is NOT
+    used (traffic = null) -- a kernel change cannot inherit the old figure silently."""
     p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     try:
         d = json.load(open(p))
     except Exception:
         return {}
-    if int(d.get("subjects_per_gpu", -1)) != int(nsub):
+    if int(d.get("subjects_per_gpu", -1)) != int(nsub) or d.get("lib_sha256") != lib_sha256():
         return {}
     return {k: v for k, v in d.get("traffic_bytes_per_launch", {}).items()}
 
@@ -131,6 +147,9 @@ def run_reference_arm(args):
         "config": {"workload": "config 3 (accelerometer 50 Hz, W=500 S=250, 16 feature columns); bounded sample per step: "
                                "1 subject-day x 3 axes (51,837 axis-windows)", "wsize": WSIZE, "wstep": WSTEP,
                    "features": STREAM_NAMES + SPECTRAL_NAMES},
+        "same_config_as_b200_arm": False,
+        "config_note": "per-window normalisation: the CPU arm processes 1 subject-day x 3 axes per step, the B200 arm 125 subject-weeks "
+                       "per GPU; both compute the same 16 columns per window",
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": "1 subject-day x 3 axes per step, %d steps; oracle port of the reference's numba path "
                                    "(the reference is pure Python + numba; /root/reference does not travel to the GPU box)" % args.steps},
@@ -199,6 +218,245 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def peak_mismatches(got_freq, x_rows, fs, wsize, wstep, lo, hi):
+    """Windows whose arg-max bin differs from the float64 reference, and whether every such window is a tie: the two
+    candidate bins' reference PSD values within 1e-5 of each other (no float32 transform can order those)."""
+    from oracle import spectral as OS
+    n_bad, all_ties, worst = 0, True, 0.0
+    for r in range(x_rows.shape[0]):
+        psd, freqs = OS.window_psd(x_rows[r], wsize, wstep, fs)
+        lidx, uidx = OS.first_index(freqs, lo), OS.first_index(freqs, hi)
+        want = lidx + np.argmax(psd[:, lidx:uidx], axis=1)
+        got = np.rint(got_freq[r][:len(want)] / freqs[1]).astype(np.int64)
+        bad = np.nonzero(got != want)[0]
+        n_bad += len(bad)
+        for i in bad:
+            a, b = psd[i, got[i]], psd[i, want[i]]
+            gap = abs(a - b) / max(b, 1e-300)
+            worst = max(worst, gap)
+            if gap > 1e-5:
+                all_ties = False
+    return n_bad, all_ties, worst
+
+
+def time_steps(torch, dist, world, dev, fn, steps, warmup):
+    """W warm-up + K timed calls of fn(), bracketed by barrier + synchronize; CUDA events; max over ranks.  ms per step."""
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.cpu()) / steps
+
+
+# ------------------------------------------------------------------------------------------------ configs[3]
+def bench_config4(torch, dist, world, rank, dev, peak, steps):
+    """500 subjects x 24 h PPG @ 64 Hz, W = 1920 / S = 64 (30 x overlap), 16 columns; the 500 subjects are split over
+    the ranks (11 GB in all), resident."""
+    from pymhealth_b200 import engine, synth, sharded, spectral as SP
+    from pymhealth_b200.generic import stats, timedom
+    W, S, fs, n = synth.PPG_WSIZE, synth.PPG_WSTEP, synth.PPG_FS, 5_529_600
+    a, b = sharded.shard_range(500, rank, world)
+    x = synth.device_ppg(b - a, n, dev, first_subject=a)
+    sf = [stats.mean.feature(), stats.std.feature(), stats.var.feature(), stats.dmin.feature(), stats.dmax.feature(),
+          stats.drange.feature(), stats.skewness.feature(), stats.kurtosis.feature(),
+          timedom.zero_crossing_count.feature(0.0), timedom.line_length.feature()]
+    bands = [(0.5, 4.0), (4.0, 8.0)]
+    pf = [SP.total_power(fs).feature(), SP.band_power(fs, *bands[0]).feature(), SP.band_power(fs, *bands[1]).feature(),
+          SP.relative_band_power(fs, *bands[0]).feature(), SP.peak_frequency(fs, 0.5, 4.0).feature(),
+          SP.spectral_entropy(fs).feature()]
+    nw = engine.n_windows(n, W, S)
+    out = torch.empty((b - a, nw, 16), dtype=torch.float32, device=dev)
+    ms_s = time_steps(torch, dist, world, dev, lambda: engine.window_table(x, W, S, sf, out=out[:, :, :10]), steps, 2)
+    ms_p = time_steps(torch, dist, world, dev, lambda: engine.window_table(x, W, S, pf, fs=fs, out=out[:, :, 10:]), steps, 2)
+    ms = time_steps(torch, dist, world, dev, lambda: engine.window_table(x, W, S, sf + pf, fs=fs, out=out), steps, 2)
+    nwin_all = 500 * nw
+    res = {"workload": "BASELINE configs[3]: 500 subjects x 24 h PPG @ 64 Hz, W=1920 S=64 (30x overlap), 16 columns; "
+                       "%d subjects on this rank, resident" % (b - a),
+           "windows": nwin_all, "ms_per_step": ms, "windows_per_s": nwin_all / (ms * 1e-3),
+           "kernels": {}}
+    if rank == 0:
+        per_rank_b = (b - a) * n * 4
+        for name, m, nc in (("window_stats (1a, k = 30)", ms_s, 10), ("spectral_w1920 (2)", ms_p, 6)):
+            alg = per_rank_b + (b - a) * nw * nc * 4
+            ach = alg / (m * 1e-3) / 1e9
+            res["kernels"][name] = {"ms_per_launch": m, "windows_per_s": nwin_all / (m * 1e-3), "achieved": ach, "unit": "GB/s",
+                                    "peak": peak, "frac": ach / peak,
+                                    "bound": "hbm" if nc == 10 else "fp32 issue (960-point FFT per 64-sample hop)"}
+        # CPU baseline + parity on a bounded sample: subject 0, first 3 h
+        import numba
+        from oracle import windows as OW, spectral as OS
+        ns = 691_200
+        sx = x[0, :ns].cpu().numpy()
+        names = STREAM_NAMES
+        OW.rolling("mean", sx[:4 * W], W, S)
+        t0 = time.perf_counter()
+        cols = [OW.rolling(k, sx, W, S, 0.0 if k == "zero_crossing_count" else None) for k in names]
+        tab = OS.spectral_table(sx, W, S, fs, bands, 0.5, 4.0)
+        dt = time.perf_counter() - t0
+        cols += [tab[k] for k in SPECTRAL_NAMES]
+        want = np.stack(cols, axis=1)
+        got = out[0, :want.shape[0]].cpu().numpy().astype(np.float64)
+        scale = np.maximum(np.abs(want), np.abs(want).mean(axis=0, keepdims=True) * 1e-3)
+        dev_cols = np.max(np.abs(got - want) / scale, axis=0)
+        pk = SPECTRAL_NAMES.index("peak_frequency") + 10
+        nb, ties, worst = peak_mismatches(got[None, :, pk], sx[None], fs, W, S, 0.5, 4.0)
+        dev_cols[pk] = 0.0 if ties else np.inf
+        res["cpu_baseline"] = {"value": want.shape[0] / dt, "unit": UNIT, "cores": numba.get_num_threads(), "kind": "port",
+                               "sample": "1 subject x 3 h (%d windows), 16 columns" % want.shape[0],
+                               "max_rel_dev_vs_gpu": float(dev_cols.max()), "peak_bin_mismatches": nb,
+                               "peak_bin_mismatches_all_ties_1e-5": ties}
+    del x, out
+    torch.cuda.empty_cache()
+    return res
+
+
+# ------------------------------------------------------------------------------------------------ configs[4]
+def bench_config5(torch, dist, world, rank, dev, peak, steps, subjects_per_gpu):
+    """10,000 subjects x 30 d x 86,400 GPS fixes: 1,250 subjects per GPU (weak scaling; 8 GPUs = the full configuration),
+    lat / lon float64 + t int64 resident (77.8 GB), one row of 11 features per subject-day, and -- at N > 1 -- the NCCL
+    gather of the [subject-days, 11] tables INSIDE the timed region."""
+    from pymhealth_b200 import sharded, synth, _lib as L
+    from pymhealth_b200.location import features as LF
+    day, ndays = 86400, 30
+    n_month = day * ndays
+    nsub = subjects_per_gpu
+    base = [synth.gps(1000 * rank + k, n_month, 1) for k in range(2)]          # two generated subject-months per rank ...
+    lat = torch.empty(nsub * n_month, dtype=torch.float64, device=dev)
+    lon = torch.empty_like(lat)
+    t = torch.empty(nsub * n_month, dtype=torch.int64, device=dev)
+    home = torch.empty((nsub * ndays, 2), dtype=torch.float64, device=dev)
+    dbase = [(torch.from_numpy(la).to(dev), torch.from_numpy(lo).to(dev), torch.from_numpy(tt).to(dev), hm) for la, lo, tt, hm in base]
+    for s in range(nsub):                                                      # ... tiled with a per-subject offset
+        la, lo, tt, hm = dbase[s % 2]
+        sl = slice(s * n_month, (s + 1) * n_month)
+        off = 1e-3 * (s // 2)
+        torch.add(la, off, out=lat[sl])
+        lon[sl] = lo
+        t[sl] = tt
+        home[s * ndays:(s + 1) * ndays, 0] = hm[0] + off
+        home[s * ndays:(s + 1) * ndays, 1] = hm[1]
+    del dbase
+    offs = torch.arange(nsub * ndays + 1, device=dev, dtype=torch.int64) * day
+    state = {}
+
+    def step():
+        rows = LF.segment_rows(lat, lon, t, offs, home)
+        state["rows"] = rows
+        state["full"] = sharded.gather_tables(rows, nsub * ndays * world) if world > 1 else rows
+    ms = time_steps(torch, dist, world, dev, step, steps, 1)
+    ms_rows = time_steps(torch, dist, world, dev, lambda: LF.segment_rows(lat, lon, t, offs, home), steps, 1)
+    ms_sd = time_steps(torch, dist, world, dev, lambda: LF.arr_successive_distance(lat, lon), steps, 1)
+    pts = world * nsub * n_month
+    res = {"workload": "BASELINE configs[4]: 10,000 subjects x 30 d GPS @ 1 Hz; %d subjects per GPU resident (weak scaling; 8 GPUs = "
+                       "the full 10,000), per-day rows of 11 features%s" % (nsub, " + NCCL all-gather of the tables in the timed region" if world > 1 else ""),
+           "points": pts, "subject_days": world * nsub * ndays, "ms_per_step": ms, "points_per_s": pts / (ms * 1e-3),
+           "rows_ms": ms_rows, "gather_ms": max(0.0, ms - ms_rows), "table_shape": list(state["full"].shape)}
+    if rank == 0:
+        alg = nsub * n_month * 24 + nsub * ndays * 88
+        ach = alg / (ms_rows * 1e-3) / 1e9
+        res["kernels"] = {"location_segments_kernel (per-day rows)": {
+                              "ms_per_launch": ms_rows, "points_per_s_per_gpu": nsub * n_month / (ms_rows * 1e-3), "achieved": ach,
+                              "unit": "GB/s", "peak": peak, "frac": ach / peak, "bound": "fp64 (haversine: one cosine + three distances per fix)"},
+                          "successive_distance_kernel (arr_successive_distance)": {
+                              "ms_per_launch": ms_sd, "achieved": nsub * n_month * 24 / (ms_sd * 1e-3) / 1e9, "unit": "GB/s", "peak": peak,
+                              "frac": nsub * n_month * 24 / (ms_sd * 1e-3) / 1e9 / peak, "bound": "fp64 / hbm"}}
+        # CPU baseline + parity on a bounded sample: subject 0, the first two days
+        from oracle import location_ext as OX
+        m = 2 * day
+        la, lo, tt = lat[:m].cpu().numpy(), lon[:m].cpu().numpy(), t[:m].cpu().numpy()
+        hm = home[:2].cpu().numpy()
+        o2 = np.array([0, day, 2 * day], dtype=np.int64)
+        OX.segment_features(la[:2000], lo[:2000], tt[:2000], np.array([0, 2000], dtype=np.int64), hm[:1], 0.1, 0.2, 1800)
+        t0 = time.perf_counter()
+        want, _ = OX.segment_features(la, lo, tt, o2, hm, 0.1, 0.2, 1800)
+        dt = time.perf_counter() - t0
+        got = state["rows"][:2].cpu().numpy()
+        res["cpu_baseline"] = {"value": m / dt, "unit": "points/s", "cores": 1, "kind": "port",
+                               "sample": "1 subject x 2 days (172,800 fixes): oracle/location_ext.segment_features (numba, one thread)",
+                               "max_rel_dev_vs_gpu": float(np.nanmax(np.abs(got - want) / np.maximum(np.abs(want), 1e-9))),
+                               "integer_columns_equal": bool(np.array_equal(got[:, [0, 5, 7, 8]], want[:, [0, 5, 7, 8]]))}
+    del lat, lon, t, home, state
+    torch.cuda.empty_cache()
+    return res
+
+
+# ------------------------------------------------------------------------------------------------ configs[0]
+def bench_config1(torch):
+    """One subject, 7 days at one fix per minute (10,080 points) through the drop-in location functions: numpy arrays in,
+    numpy arrays / scalars out (every call pays its own H2D / D2H), beside the oracle port of the reference functions."""
+    from pymhealth_b200 import synth
+    from pymhealth_b200.location import features as LF, distribution as LD
+    from oracle import location as OL, location_ext as OX
+    n = 10_080
+    lat, lon, t, home = synth.gps(0, n, 60)
+
+    def gpu_calls():
+        d = LF.arr_successive_distance(lat, lon)
+        h = LF.arr_distance_from_home(lat, lon, home)
+        p = LF.arr_proportion_home_stay(lat, lon, 0.1, home)
+        v = LD.arr_location_variance(lat, lon)
+        g = LF.radius_of_gyration(lat, lon)
+        lab = LF.stay_points(lat, lon, t, 0.2, 1800)
+        e = LD.cluster_entropy(lab)
+        return d, h, p, v, g, lab, e
+
+    def cpu_calls():
+        d = OL.arr_successive_distance(lat, lon)
+        h = OL.arr_distance_from_home(lat, lon, home)
+        p = OL.arr_proportion_home_stay(lat, lon, 0.1, home)
+        v = OL.arr_location_variance(lat, lon)
+        g = OX.radius_of_gyration(lat, lon)
+        lab = OX.stay_points(lat, lon, t, 0.2, 1800)
+        e = OL.cluster_entropy(lab)
+        return d, h, p, v, g, lab, e
+    g = gpu_calls()
+    c = cpu_calls()
+    torch.cuda.synchronize()
+    reps = 20
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        gpu_calls()
+    torch.cuda.synchronize()
+    tg = (time.perf_counter() - t0) / reps
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        cpu_calls()
+    tc = (time.perf_counter() - t0) / reps
+    rows_ms = None
+    o = np.array([0, n], dtype=np.int64)
+    hm = np.array([home], dtype=np.float64)
+    LF.segment_rows(lat, lon, t, o, hm)
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        LF.segment_rows(lat, lon, t, o, hm)
+    rows_ms = (time.perf_counter() - t0) / reps * 1e3
+    devs = [float(np.max(np.abs(np.asarray(a, dtype=np.float64) - np.asarray(b, dtype=np.float64)) /
+                         np.maximum(np.abs(np.asarray(b, dtype=np.float64)), 1e-9))) for a, b in zip(g[:5], c[:5])]
+    return {"workload": "BASELINE configs[0]: 1 subject x 7 d GPS @ 1/min (10,080 fixes): successive distance, distance from home, "
+                        "home-stay proportion, location variance, radius of gyration, stay points, label entropy -- seven drop-in calls, "
+                        "host arrays in / out",
+            "points": n, "gpu_ms_seven_calls": tg * 1e3, "gpu_points_per_s": n / tg, "gpu_ms_one_launch_rows": rows_ms,
+            "cpu_baseline": {"value": n / tc, "unit": "points/s", "cores": 1, "kind": "port", "ms": tc * 1e3,
+                             "sample": "the same seven functions, oracle port (numba, one thread; the reference's gufuncs are single-threaded)"},
+            "max_rel_dev_vs_cpu": max(devs), "stay_labels_equal": bool(np.array_equal(g[5], c[5])),
+            "label_entropy_rel_dev": float(abs(g[6] - c[6]) / max(abs(c[6]), 1e-12)),
+            "note": "a latency-sized job: every call is dominated by launch + PCIe round trips"}
+
+
+# ------------------------------------------------------------------------------------------------ headline: configs[2]
 def run_b200_arm(args):
     import torch
     import torch.distributed as dist
@@ -218,6 +476,8 @@ def run_b200_arm(args):
         dist.init_process_group("nccl", device_id=dev)
     if args.gpus != world and rank == 0:
         print("note: --gpus %d but WORLD_SIZE=%d; reporting n_gpus=%d" % (args.gpus, world, world), file=sys.stderr)
+    numa_node = sharded.bind_host_to_device_numa(local)        # pinned buffers next to this GPU's PCIe root (before any allocation)
+    peak, peak_src = measured_peak_gbs()
 
     nsub = args.subjects_per_gpu
     n = args.samples
@@ -270,100 +530,89 @@ def run_b200_arm(args):
     total_ms, ms_stats, ms_spec = (float(v) for v in tmax.cpu())
     value = world * windows_per_step * args.steps / (total_ms * 1e-3)
 
-    # ---- outside the timed step: the order-statistics kernel (kernel 1b: median + 90th percentile) on a slice of the
-    # shard, reported next to the step's kernels (percentiles are part of the north-star feature list; the 16 bench
-    # columns, fixed in BASELINE.md's plan, hold none)
-    ms_order, order_series = None, min(24, nsub * 3)
-    if rank == 0:
-        from pymhealth_b200.generic import stats as _st
-        order_f = [_st.median.feature(), _st.percentile.feature(90.0)]
-        t_ord = torch.empty((order_series, nw, 2), dtype=torch.float32, device=dev)
-        engine.window_table(x[:order_series], WSIZE, WSTEP, order_f, out=t_ord)
-        o0, o1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        torch.cuda.synchronize()
-        o0.record()
-        for _ in range(3):
-            engine.window_table(x[:order_series], WSIZE, WSTEP, order_f, out=t_ord)
-        o1.record()
-        torch.cuda.synchronize()
-        ms_order = o0.elapsed_time(o1) / 3
-        del t_ord
+    # ---- the same step with the order statistics of the north-star list in it: kernel 1b (median + 90th percentile) over
+    # the WHOLE shard, 18 columns per window
+    from pymhealth_b200.generic import stats as _st
+    order_f = [_st.median.feature(), _st.percentile.feature(90.0)]
+    t_ord = torch.empty((nsub * 3, nw, 2), dtype=torch.float32, device=dev)
+    ms_order = time_steps(torch, dist, world, dev, lambda: engine.window_table(x, WSIZE, WSTEP, order_f, out=t_ord),
+                          max(2, args.steps // 3), 1)
+    ms_step18 = total_ms / args.steps + ms_order
+    value18 = world * windows_per_step / (ms_step18 * 1e-3)
+    del t_ord
 
-    # ---- also outside the step: kernel 1a in magnitude mode -- the same 10 streaming columns of
+    # ---- multi-GPU equality: rank r regenerates the first 8 subjects of rank r + 1 (same seeds, same
+    # generator launch shapes), recomputes subject 0's table and compares it, bit for bit, with the rows the owner sends
+    equality = None
+    if world > 1:
+        other = (rank + 1) % world
+        xo = synth.device_accelerometer(min(8, nsub), n, dev, first_subject=other * nsub).view(-1, n)[:3]
+        mine_of_other = engine.window_table(xo, WSIZE, WSTEP, feats, fs=FS)
+        own = table[:3].contiguous()
+        gathered = torch.empty((world,) + tuple(own.shape), dtype=own.dtype, device=dev)
+        dist.all_gather_into_tensor(gathered, own)
+        same = torch.tensor([1 if torch.equal(gathered[other], mine_of_other) else 0], device=dev)
+        dist.all_reduce(same, op=dist.ReduceOp.MIN)
+        equality = bool(int(same.cpu()))
+        assert equality, "tables of the same subject differ between ranks"
+        del xo, mine_of_other, gathered
+
+    # ---- kernel 1a in magnitude mode, outside the step -- the same 10 streaming columns of
     # magnitude(x, y, z), the three axis planes combined inside the TMA-staged tile (12 B of samples per magnitude)
     ms_mag, mag_sub = None, min(32, nsub)
     if rank == 0:
         x3 = x.view(nsub, 3, n)[:mag_sub]
         t_mag = torch.empty((mag_sub, nw, len(stream_f)), dtype=torch.float32, device=dev)
-        engine.magnitude_window_table(x3[:, 0], x3[:, 1], x3[:, 2], WSIZE, WSTEP, stream_f, out=t_mag)
-        o0, o1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        torch.cuda.synchronize()
-        o0.record()
-        for _ in range(3):
-            engine.magnitude_window_table(x3[:, 0], x3[:, 1], x3[:, 2], WSIZE, WSTEP, stream_f, out=t_mag)
-        o1.record()
-        torch.cuda.synchronize()
-        ms_mag = o0.elapsed_time(o1) / 3
+        ms_mag = time_steps(torch, dist, 1, dev, lambda: engine.magnitude_window_table(x3[:, 0], x3[:, 1], x3[:, 2], WSIZE, WSTEP,
+                                                                                      stream_f, out=t_mag), 3, 1)
         del t_mag
 
-    # ---- end-to-end through the public host-buffer API (pinned host inputs, H2D + kernels + D2H per step)
+    # ---- end-to-end through the public host-buffer API: pinned host inputs as the RAW int16 counts a logger stores
+    # (1 / 4096 g per count; 2 bytes per sample over PCIe, widened on the device -- exact), H2D + kernels + D2H per step
     e2e_sub = min(args.e2e_subjects, nsub)
-    numa_node = sharded.bind_host_to_device_numa(local)        # pinned buffers next to this GPU's PCIe root
-    hx = torch.empty((e2e_sub * 3, n), dtype=torch.float32).pin_memory()
-    hx.copy_(x[:e2e_sub * 3])
+    scale = 1.0 / 4096.0
+    counts = torch.round(x[:e2e_sub * 3] * 4096.0).clamp_(-32768, 32767).to(torch.int16)
+    hx = torch.empty((e2e_sub * 3, n), dtype=torch.int16).pin_memory()
+    hx.copy_(counts)
     hout = torch.empty((e2e_sub * 3, nw, nf), dtype=torch.float32).pin_memory()
-    pipe = FeaturePipeline(feats, WSIZE, WSTEP, fs=FS, chunk_series=3)
+    pipe = FeaturePipeline(feats, WSIZE, WSTEP, fs=FS, chunk_series=3, count_scale=scale)
     pipe.run(hx, hout)
-    torch.cuda.synchronize()
-    check_ok = bool(torch.allclose(hout, table[:e2e_sub * 3].cpu(), rtol=1e-5, atol=1e-6, equal_nan=True))   # same kernels
-    if world > 1:
-        dist.barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    xq = counts.float() * scale
+    # same values, same kernels (the chunking of kernel 1a -- hence its float64 pivots -- differs between the 3-series chunks
+    # of the pipeline and the whole batch, so float columns agree to rounding, integer-valued ones exactly)
+    ref_t = engine.window_table(xq, WSIZE, WSTEP, feats, fs=FS).cpu()
+    exact_cols = [STREAM_NAMES.index(k) for k in ("min", "max", "drange", "zero_crossing_count")]
+    check_ok = bool(torch.allclose(hout, ref_t, rtol=1e-6, atol=1e-7, equal_nan=True)) and \
+        bool(torch.equal(hout[:, :, exact_cols], ref_t[:, :, exact_cols]))
+    del ref_t
+    del counts, xq
     e2e_steps = 3
-    torch.cuda.synchronize()
-    e0.record()
-    for _ in range(e2e_steps):
-        pipe.run(hx, hout)
-    e1.record()
-    torch.cuda.synchronize()
-    e2e_ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
-    e2e_value = world * e2e_sub * 3 * nw * e2e_steps / (float(e2e_ms.cpu()) * 1e-3)
+    e2e_ms = time_steps(torch, dist, world, dev, lambda: pipe.run(hx, hout), e2e_steps, 1)
+    e2e_value = world * e2e_sub * 3 * nw / (e2e_ms * 1e-3)
+    # the ceiling of this box for that feed: all ranks copy the same pinned buffer host -> device at the same time
+    dtmp = torch.empty_like(hx, device=dev)
+    h2d_ms = time_steps(torch, dist, world, dev, lambda: dtmp.copy_(hx, non_blocking=True), 3, 1)
+    h2d_gbs_rank = hx.numel() * 2 / (h2d_ms * 1e-3) / 1e9
+    del dtmp
 
     # ---- BASELINE configs[1], reported beside the headline: ONE subject x 24 h x 3 axes (4.32 M samples per axis, 51,837
-    # axis-windows) -- a latency-sized job: resident (both kernels, 16 columns) and through the host-buffer API
+    # axis-windows) -- a latency-sized job: resident (16 columns) and through the host-buffer API
     single = None
     if rank == 0:
         n1 = 4_320_000
         nw1 = engine.n_windows(n1, WSIZE, WSTEP)
         x1 = x[:3, :n1]
         t1 = torch.empty((3, nw1, nf), dtype=torch.float32, device=dev)
-
-        def step1():
-            engine.window_table(x1, WSIZE, WSTEP, stream_f, out=t1[:, :, :len(stream_f)])
-            engine.window_table(x1, WSIZE, WSTEP, spec_f, fs=FS, out=t1[:, :, len(stream_f):])
-        for _ in range(3):
-            step1()
-        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        torch.cuda.synchronize()
-        s0.record()
-        for _ in range(20):
-            step1()
-        s1.record()
-        torch.cuda.synchronize()
-        ms1 = s0.elapsed_time(s1) / 20
+        ms1 = time_steps(torch, dist, 1, dev, lambda: engine.window_table(x1, WSIZE, WSTEP, feats, fs=FS, out=t1), 20, 3)
         hx1 = torch.empty((3, n1), dtype=torch.float32).pin_memory()
         hx1.copy_(x1)
         ho1 = torch.empty((3, nw1, nf), dtype=torch.float32).pin_memory()
         pipe1 = FeaturePipeline(feats, WSIZE, WSTEP, fs=FS, chunk_series=3)
         for _ in range(2):
             pipe1.run(hx1, ho1)
-        torch.cuda.synchronize()
         w0_ = time.perf_counter()
         for _ in range(10):
             pipe1.run(hx1, ho1)
-        torch.cuda.synchronize()
         e2e1 = (time.perf_counter() - w0_) / 10 * 1e3
         single = {"workload": "BASELINE configs[1]: 1 subject x 24 h x 3 axes @ 50 Hz, W=500 S=250, 16 columns",
                   "axis_windows": 3 * nw1, "resident_ms": ms1, "resident_windows_per_s": 3 * nw1 / (ms1 * 1e-3),
@@ -371,23 +620,48 @@ def run_b200_arm(args):
                   "h2d_bytes": int(hx1.numel() * 4), "d2h_bytes": int(ho1.numel() * 4)}
         del t1, hx1, ho1
 
-    # ---- the one collective of the design: gather per-subject summary rows (mean of every column over the week)
+    # ---- gather of per-subject summary rows (mean of every column over the week); outside the config-3 step, whose
+    # full table (23 GB at 8 GPUs) stays sharded
     summary = table.view(nsub, 3 * nw, nf).mean(dim=1)
     gather_ms = 0.0
     if world > 1:
-        torch.cuda.synchronize()
-        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        g0.record()
-        full = sharded.gather_tables(summary, nsub * world)
-        g1.record()
-        torch.cuda.synchronize()
-        gather_ms = g0.elapsed_time(g1)
-        assert tuple(full.shape) == (nsub * world, nf)
+        gather_ms = time_steps(torch, dist, world, dev, lambda: sharded.gather_tables(summary, nsub * world), 3, 1)
+
+    # ---- CPU baseline / parity sample for config 3 (rank 0, N = 1 only), taken before the shard is released
+    cpu3 = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        import numba
+        sx = x[:3].cpu().numpy()                                   # 1 subject x 3 axes x 7 d
+        if args.cpu_sample_samples and args.cpu_sample_samples < n:
+            sx = np.ascontiguousarray(sx[:, :args.cpu_sample_samples])
+        warm_oracle()
+        dt, nwin, tab = oracle_features(sx, want_table=True)
+        got = table[:3, :tab.shape[1]].cpu().numpy().astype(np.float64)
+        scale_c = np.maximum(np.abs(tab), np.abs(tab).mean(axis=(0, 1), keepdims=True) * 1e-3)
+        dev_c = np.abs(got - tab) / scale_c
+        pk = len(stream_f) + SPECTRAL_NAMES.index("peak_frequency")
+        nb, ties, worst = peak_mismatches(got[:, :, pk], sx, FS, WSIZE, WSTEP, PEAK[0], PEAK[1])
+        dev_c[:, :, pk] = 0.0                                       # judged as bins: exact, or a counted tie
+        assert ties, "a peak bin differs from the reference beyond a 1e-5 tie (worst gap %g)" % worst
+        cpu3 = {"value": nwin / dt, "unit": UNIT, "cores": numba.get_num_threads(), "kind": "port", "seconds": dt,
+                "sample": "1 subject x 3 axes x %d samples (%d axis-windows), 16 columns, one rolling pass per statistical "
+                          "reducer + numpy FFT; numba prange on all host threads" % (sx.shape[1], nwin),
+                "max_rel_dev_vs_gpu": float(dev_c.max()), "peak_bin_mismatches": nb, "peak_bin_mismatches_all_ties_1e-5": ties,
+                "peak_bin_worst_tie_gap": worst}
+
+    del x, table, t_stats, t_spec, summary, hx, hout
+    torch.cuda.empty_cache()
+
+    # ---- the other BASELINE configurations (each timed like the headline: resident, CUDA events, max over ranks)
+    c4 = c5 = c1 = None
+    if not args.headline_only:
+        c4 = bench_config4(torch, dist, world, rank, dev, peak, 3)
+        c5 = bench_config5(torch, dist, world, rank, dev, peak, 3, args.gps_subjects_per_gpu)
+        if rank == 0:
+            c1 = bench_config1(torch)
 
     if rank == 0:
-        peak, peak_src = measured_peak_gbs()
         samples_b = nsub * 3 * n * 4
-
         traffic = ncu_traffic(nsub)
 
         def roof(name, key, ms, ncols):
@@ -397,15 +671,16 @@ def run_b200_arm(args):
                     "traffic": traffic.get(key), "ms_per_launch": ms, "algorithmic_bytes": alg, "peak_source": peak_src}
         k_stats = roof("window_stats_kernel (kernel 1a)", "window_stats", ms_stats, len(stream_f))
         k_spec = roof("spectral_fast_kernel (kernel 2)", "window_spectral", ms_spec, len(spec_f))
-        dominant = k_spec if ms_spec >= ms_stats else k_stats
-        dominant = dict(dominant)
+        k_ord = roof("window_order_blocks_kernel (kernel 1b: median + p90)", "window_order", ms_order, 2)
+        k_ord["bound"] = "sm (sorting / selection)"
+        dominant = dict(k_spec if ms_spec >= ms_stats else k_stats)
         if dominant["kernel"].startswith("spectral"):
-            # FP32 lane-instructions the transform needs at the very least: ~16e3 per window
-            fp32_peak = 148 * 128 * (clocks or {}).get("sm_mhz", 1965.0) * 1e6 if clocks else 148 * 128 * 1965e6
-            dominant["note"] = ("kernel 2 is FP32-issue-bound (a 250-point complex FFT + PSD reducers per 1,000 B window is >= ~16e3 "
-                                "lane-instructions; 100 % FP32 issue would be ~35 % of HBM peak), not HBM-bound; frac is its HBM "
+            dominant["note"] = ("kernel 2 is bound by FP32 issue / latency, not by HBM: a 250-point complex FFT + PSD reducers per "
+                                "1,000-byte window is ~12.6e3 FP32 lane-operations (98 SM-cycles of the FMA pipe); frac is its HBM "
                                 "fraction all the same.  kernel 1a (HBM-bound) is listed under 'kernels'.")
-            dominant["fp32_issue_floor_frac"] = (windows_per_step * 16e3 / fp32_peak) / (ms_spec * 1e-3)
+            fp32_peak = 148 * 128 * ((clocks or {}).get("sm_mhz") or 1965.0) * 1e6
+            dominant["fma_pipe_frac"] = (windows_per_step * 12.6e3 / fp32_peak) / (ms_spec * 1e-3)
+        step_alg = samples_b + windows_per_step * nf * 4
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -416,14 +691,13 @@ def run_b200_arm(args):
                        "feature_columns": nf, "features": STREAM_NAMES + SPECTRAL_NAMES, "wsize": WSIZE, "wstep": WSTEP,
                        "l2": "inputs (%.1f GB per GPU) are far larger than the 126 MB L2; no flush needed" % (samples_b / 1e9),
                        "parallelism": "subject-sharded x%d, no data-path collective" % world},
+            "value_with_order": value18, "ms_per_step_with_order": ms_step18,
+            "whole_step": {"algorithmic_bytes": step_alg, "achieved": step_alg / (total_ms / args.steps * 1e-3) / 1e9, "unit": "GB/s",
+                           "frac": step_alg / (total_ms / args.steps * 1e-3) / 1e9 / peak,
+                           "note": "each sample counted once, 16 output cells per window (SURVEY 8d: 1,064 B per window); the step "
+                                   "is two launches, so its DRAM traffic is 2x the samples"},
             "roofline": dominant,
-            "kernels": {"window_stats": k_stats, "window_spectral": k_spec,
-                        "window_order (not in the step)": {
-                            "kernel": "window_order_blocks_kernel (kernel 1b: median + p90)", "bound": "sm (sorting)",
-                            "series": order_series, "ms_per_launch": ms_order,
-                            "windows_per_s": order_series * nw / (ms_order * 1e-3) if ms_order else None,
-                            "achieved": (order_series * n * 4 + order_series * nw * 8) / (ms_order * 1e-3) / 1e9 if ms_order else None,
-                            "unit": "GB/s"},
+            "kernels": {"window_stats": k_stats, "window_spectral": k_spec, "window_order": k_ord,
                         "window_stats magnitude mode (not in the step)": {
                             "kernel": "window_stats_kernel<MAG> (kernel 1a on magnitude(x, y, z), axes fused in the staged tile)",
                             "bound": "hbm", "subjects": mag_sub, "ms_per_launch": ms_mag,
@@ -431,35 +705,32 @@ def run_b200_arm(args):
                             "achieved": (mag_sub * n * 12 + mag_sub * nw * len(stream_f) * 4) / (ms_mag * 1e-3) / 1e9 if ms_mag else None,
                             "peak": peak, "unit": "GB/s",
                             "frac": ((mag_sub * n * 12 + mag_sub * nw * len(stream_f) * 4) / (ms_mag * 1e-3) / 1e9 / peak) if ms_mag else None}},
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(hx.numel() * 4),
-                    "d2h_bytes_per_step": int(hout.numel() * 4), "subjects_per_step_per_gpu": e2e_sub,
-                    "ms_per_step": float(e2e_ms.cpu()) / e2e_steps, "matches_resident_run": check_ok,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(hx_numel(e2e_sub, n) * 2),
+                    "d2h_bytes_per_step": int(e2e_sub * 3 * nw * nf * 4), "subjects_per_step_per_gpu": e2e_sub,
+                    "ms_per_step": e2e_ms, "matches_resident_run": check_ok, "input": "int16 raw counts (1/4096 g), pinned",
                     "api": "pymhealth_b200.pipeline.FeaturePipeline.run (pinned host in, pinned host out)",
-                    "host_numa_node_rank0": numa_node},
+                    "host_numa_node_rank0": numa_node,
+                    "h2d_ceiling": {"what": "all ranks copy the same pinned int16 buffer host -> device at once (plain cudaMemcpyAsync)",
+                                    "ms": h2d_ms, "GB/s_per_rank": h2d_gbs_rank, "GB/s_all_ranks": h2d_gbs_rank * world,
+                                    "windows_per_s_at_that_rate": world * e2e_sub * 3 * nw / (h2d_ms * 1e-3)}},
             "single_subject_24h": single,
+            "multi_gpu_tables_equal": equality,
+            "config4_ppg": c4, "config5_gps": c5, "config1_gps": c1,
             "gpu_launches": 2 * args.steps,
             "clocks": clocks,
             "gather_ms": gather_ms,
         }
-        if world == 1 and not args.no_cpu_baseline:
-            import numba
-            sx = x[:3].cpu().numpy()                                   # 1 subject x 3 axes x 7 d
-            if args.cpu_sample_samples and args.cpu_sample_samples < n:
-                sx = np.ascontiguousarray(sx[:, :args.cpu_sample_samples])
-            warm_oracle()
-            dt, nwin, tab = oracle_features(sx, want_table=True)
-            got = table[:3, :tab.shape[1]].cpu().numpy().astype(np.float64)
-            scale = np.maximum(np.abs(tab), np.abs(tab).mean(axis=(0, 1), keepdims=True) * 1e-3)
-            line["cpu_baseline"] = {"value": nwin / dt, "unit": UNIT, "cores": numba.get_num_threads(), "kind": "port",
-                                    "seconds": dt,
-                                    "sample": "1 subject x 3 axes x %d samples (%d axis-windows), 16 columns, one rolling pass per "
-                                              "statistical reducer + numpy FFT; numba prange on all host threads" % (sx.shape[1], nwin),
-                                    "max_rel_dev_vs_gpu": float(np.max(np.abs(got - tab) / scale))}
+        if cpu3 is not None:
+            line["cpu_baseline"] = cpu3
         emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
     return 0
+
+
+def hx_numel(e2e_sub, n):
+    return e2e_sub * 3 * n
 
 
 def _claim_stdout():
@@ -492,6 +763,8 @@ def main():
     ap.add_argument("--e2e-subjects", type=int, default=8)
     ap.add_argument("--cpu-sample-samples", type=int, default=0, help="truncate the CPU-baseline sample (debug)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--headline-only", action="store_true", help="skip the config 4 / 5 / 1 sections (ncu launch lists)")
+    ap.add_argument("--gps-subjects-per-gpu", type=int, default=int(os.environ.get("MHB_BENCH_GPS_SUBJECTS", "1250")))
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3                      # timing rule: at least 3 warm-up steps

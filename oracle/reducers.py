@@ -43,21 +43,31 @@ def w_std(w):
 
 @njit(cache=True)
 def w_min(w):
-    # stats.py:161 (np.min); NaN-free inputs assumed (numba's np.min propagates NaN)
+    # stats.py:161 (np.min): numba's array min propagates NaN (numba/np/arraymath.py, "if np.isnan(v): return v")
     m = w[0]
+    if np.isnan(m):
+        return m
     for i in range(1, w.shape[0]):
-        if w[i] < m:
-            m = w[i]
+        v = w[i]
+        if np.isnan(v):
+            return v
+        if v < m:
+            m = v
     return m
 
 
 @njit(cache=True)
 def w_max(w):
-    # stats.py:162 (np.max)
+    # stats.py:162 (np.max): NaN propagates, as in numba's array max
     m = w[0]
+    if np.isnan(m):
+        return m
     for i in range(1, w.shape[0]):
-        if w[i] > m:
-            m = w[i]
+        v = w[i]
+        if np.isnan(v):
+            return v
+        if v > m:
+            m = v
     return m
 
 

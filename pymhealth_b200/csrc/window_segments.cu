@@ -281,14 +281,27 @@ namespace {
 
 // ---- get_indices: left searchsorted of first + i*step (starts) and first + i*step + size (ends)
 template <typename T>
+__device__ __forceinline__ T arange_key(T first, T step, int64_t i);
+template <>
+__device__ __forceinline__ int64_t arange_key<int64_t>(int64_t first, int64_t step, int64_t i) { return first + i * step; }
+template <>
+__device__ __forceinline__ double arange_key<double>(double first, double step, int64_t i) {
+    const double second = __dadd_rn(first, step);
+    if (i == 0) return first;
+    if (i == 1) return second;
+    return __dadd_rn(first, __dmul_rn(static_cast<double>(i), __dsub_rn(second, first)));
+}
+
+template <typename T>
 __global__ void get_indices_kernel(const T* __restrict__ index, int64_t n, T first, T wsize, T wstep, int64_t nwin,
                                    int64_t* __restrict__ out) {
     const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i >= 2 * nwin) return;
     const int64_t wi = i < nwin ? i : i - nwin;
-    // np.arange(start, stop, step)[i] = start + i * delta: exact for integers; for floats numpy fills with
-    // delta = (start + step) - start in float64, which the host passes as `wstep` (engine.device_get_indices)
-    T key = first + static_cast<T>(wi) * wstep;
+    // np.arange(start, stop, step)[i]: exact for integers.  For floats numpy stores start and start + step, then FILLS
+    // the rest as start + i * delta with delta = (start + step) - start -- not always the same double as step
+    // (0.1, 0.2 -> 0.20000000000000004) -- each operation rounded on its own (no FMA contraction)
+    T key = arange_key<T>(first, wstep, wi);
     if (i >= nwin) key = key + wsize;
     int64_t lo = 0, hi = n;                  // first position with index[pos] >= key  (side='left')
     while (lo < hi) {

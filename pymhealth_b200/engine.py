@@ -299,10 +299,8 @@ def device_get_indices(index, wsize, wstep):
     out = torch.empty((2, nwin), dtype=torch.int64, device=it.device)
     if nwin:
         fn = lib.mhb_get_indices_f64 if is_f else lib.mhb_get_indices_i64
-        # numpy fills a float arange as start + i * delta with delta = (start + step) - start, not always the same
-        # double as step (start = 0.1, step = 0.2 -> 0.20000000000000004): keys on window boundaries depend on it
-        kstep = (first + wstep) - first if is_f else wstep
-        st = fn(it.data_ptr(), n, first, wsize, kstep, nwin, out.data_ptr(), _stream_ptr(torch))
+        # (float keys: the kernel reproduces numpy's arange fill, start + i * ((start + step) - start), itself)
+        st = fn(it.data_ptr(), n, first, wsize, wstep, nwin, out.data_ptr(), _stream_ptr(torch))
         L.check(st, "get_indices")
     return out
 

@@ -7,25 +7,29 @@ GPUs (NVLink 5 / NVSwitch) or gloo in the CPU tests.  One process per GPU, torch
 """
 
 
+def device_numa_node(device_index):
+    """NUMA node of the GPU's PCIe root, from sysfs via the bus id torch reports (no pynvml needed); None when the
+    box has a single node or does not say (numa_node = -1, containers without /sys)."""
+    import torch
+    try:
+        pr = torch.cuda.get_device_properties(int(device_index))
+        bus = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        with open("/sys/bus/pci/devices/%s/numa_node" % bus) as f:
+            node = int(f.read().strip())
+        return node if node >= 0 else None
+    except Exception:
+        return None
+
+
 def bind_host_to_device_numa(device_index):
     """Pin this process to the CPUs of the NUMA node the GPU hangs off, so that pinned host buffers allocated
     afterwards (first touch) live next to the GPU's PCIe root: with one process per GPU, eight ranks pulling 54 GB/s
     each otherwise meet on the cross-socket link.  Best effort: returns the node id, or None when the topology cannot
-    be read (no sysfs, a single node, pynvml missing)."""
+    be read or the box has one node (then there is nothing to bind)."""
     import os
     try:
-        import pynvml
-        pynvml.nvmlInit()
-        h = pynvml.nvmlDeviceGetHandleByIndex(int(device_index))
-        bus = pynvml.nvmlDeviceGetPciInfo(h).busId
-        if isinstance(bus, bytes):
-            bus = bus.decode()
-        bus = bus.lower()
-        if len(bus.split(":")[0]) == 8:                 # "00000000:1b:00.0" -> "0000:1b:00.0"
-            bus = bus[4:]
-        with open("/sys/bus/pci/devices/%s/numa_node" % bus) as f:
-            node = int(f.read().strip())
-        if node < 0:
+        node = device_numa_node(device_index)
+        if node is None:
             return None
         with open("/sys/devices/system/node/node%d/cpulist" % node) as f:
             spec = f.read().strip()

@@ -171,3 +171,20 @@ def test_extra_oracles_pinned():
     assert abs(OH.rmssd(rr) - float(ref["hrv/rmssd"])) <= 1e-12 * float(ref["hrv/rmssd"])
     assert abs(OH.ssd(rr) - float(ref["hrv/ssd"])) <= 1e-9
     assert abs(OH.sdsd(rr) - float(ref["hrv/sdsd"])) <= 1e-12 * float(ref["hrv/sdsd"])
+
+
+def test_oracle_min_max_propagate_nan_like_numba():
+    """The reference's np.min / np.max run inside numba, whose array min / max return NaN as soon as one is met; the
+    restatement must do the same (the GPU kernels use FMNMX.NAN for it)."""
+    import numba
+
+    @numba.njit
+    def ref(a):
+        return np.min(a), np.max(a)
+    rng = np.random.default_rng(3)
+    for trial in range(20):
+        w = rng.standard_normal(17)
+        if trial % 4:
+            w[rng.integers(0, 17)] = np.nan
+        lo, hi = ref(w)
+        np.testing.assert_array_equal([OR.w_min(w), OR.w_max(w)], [lo, hi])

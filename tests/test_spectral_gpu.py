@@ -53,8 +53,10 @@ def test_golden_spectral(ref_spectral, case, monkeypatch):
     psd_ref, freqs = OS.window_psd(x, W, S, fs)
     lidx, uidx = OS.first_index(freqs, 0.3), OS.first_index(freqs, 12.0)
     _check_peaks(got["peak_bin"].astype(np.int64), psd_ref, lidx, uidx, "peak bin")
-    same = got["peak"] == ref_spectral[case + "/peak_frequency_0.3_12"]
-    assert same.mean() > 0.9
+    # the frequency column against the reference's own values: equal, except where the bin check above found a tie
+    ties = got["peak_bin"].astype(np.int64) != (lidx + np.argmax(psd_ref[:, lidx:uidx], axis=1))
+    np.testing.assert_array_equal(got["peak"][~ties], ref_spectral[case + "/peak_frequency_0.3_12"][~ties])
+    assert ties.sum() <= max(1, len(ties) // 100), "%d of %d windows are arg-max ties" % (ties.sum(), len(ties))
     np.testing.assert_array_equal(got["peak"], freqs[got["peak_bin"].astype(np.int64)])
     _check_peaks(np.round(got["peak_all"] / freqs[1]).astype(np.int64), psd_ref, 0, len(freqs), "peak all")
     # raw PSD rows

@@ -169,3 +169,37 @@ def test_integer_sensor_counts():
                 np.testing.assert_array_equal(g, want, err_msg="%s %s" % (dt.__name__, name))
             else:
                 np.testing.assert_allclose(g, want, rtol=1e-9, atol=1e-9, err_msg="%s %s" % (dt.__name__, name))
+
+
+@pytest.mark.parametrize("n,W,S", [(40000, 500, 250), (60000, 1920, 64), (9000, 64, 48), (5000, 100, 100)])
+def test_non_finite_samples_stay_local(n, W, S):
+    """Sensor gaps stored as NaN (and a stray inf): only the windows that CONTAIN such a sample may be affected, and they
+    must propagate exactly as the reference's numpy reducers do (np.min / np.max return NaN, a crossing with NaN is
+    "not positive").  The first sample of the series (the pivot of the shifted power sums) is one of them."""
+    from oracle import windows as OW
+    from pymhealth_b200.util import rolling_apply
+    R = _reducers()
+    rng = np.random.default_rng(W + S)
+    x = (0.8 + 0.3 * rng.standard_normal(n)).astype(np.float32)
+    bad = np.array([0, 7 * S + 3, n // 2, n // 2 + 1, n - 1])
+    x[bad] = np.nan
+    x[n // 3] = np.inf
+    x[2 * n // 3] = -np.inf
+    names = ["mean", "var", "std", "min", "max", "drange", "skewness", "kurtosis", "zero_crossing_count", "line_length"]
+    got = rolling_apply([R[k] for k in names])(x, W, S)
+    nw = 1 + (n - W) // S
+    starts = np.arange(nw) * S
+    touched = np.zeros(nw, dtype=bool)
+    for b in list(bad) + [n // 3, 2 * n // 3]:
+        touched |= (starts <= b) & (b < starts + W)
+    assert touched.sum() < nw // 2
+    for name, g in zip(names, got):
+        want = OW.rolling(name, x, W, S, 0.0 if name == "zero_crossing_count" else None)
+        clean = ~touched
+        assert np.all(np.isfinite(g[clean])), name                       # nothing leaks into the other windows
+        assert_feature_close(name, g[clean], want[clean], x[np.isfinite(x)], RTOL_TIGHT)
+        if name in ("min", "max", "zero_crossing_count"):                 # exact propagation where the reference defines it
+            np.testing.assert_array_equal(g[touched], want[touched], err_msg=name)
+        elif name in ("mean", "line_length"):
+            np.testing.assert_array_equal(np.isnan(g[touched]), np.isnan(want[touched]), err_msg=name)
+            np.testing.assert_array_equal(np.isposinf(g[touched]), np.isposinf(want[touched]), err_msg=name)

@@ -1,9 +1,12 @@
 #!/usr/bin/env python3
 """Extract per-launch DRAM traffic of the bench kernels from `ncu --set full` reports taken at bench shard size.
-usage: python tools/ncu_traffic.py NSUB stats.ncu-rep spec.ncu-rep > profiles/ncu_traffic.json"""
+usage: python tools/ncu_traffic.py NSUB stats.ncu-rep spec.ncu-rep [order.ncu-rep] > profiles/ncu_traffic.json
+The output names the sha256 of the libmhb200.so in the tree: bench.py uses the figures only for that very build."""
 import csv
+import hashlib
 import io
 import json
+import os
 import subprocess
 import sys
 
@@ -27,10 +30,17 @@ def traffic(rep):
 def main():
     nsub = int(sys.argv[1])
     st, sp = traffic(sys.argv[2]), traffic(sys.argv[3])
-    json.dump({"subjects_per_gpu": nsub, "source": "ncu --set full --clock-control none, one launch each at bench shard size",
-               "traffic_bytes_per_launch": {"window_stats": st["dram_read"] + st["dram_write"],
-                                            "window_spectral": sp["dram_read"] + sp["dram_write"]},
-               "detail": {"window_stats": st, "window_spectral": sp}}, sys.stdout, indent=1)
+    lib = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "pymhealth_b200", "libmhb200.so")
+    out = {"subjects_per_gpu": nsub, "lib_sha256": hashlib.sha256(open(lib, "rb").read()).hexdigest(),
+           "source": "ncu --set full --clock-control none, one launch each at bench shard size",
+           "traffic_bytes_per_launch": {"window_stats": st["dram_read"] + st["dram_write"],
+                                        "window_spectral": sp["dram_read"] + sp["dram_write"]},
+           "detail": {"window_stats": st, "window_spectral": sp}}
+    if len(sys.argv) > 4:
+        od = traffic(sys.argv[4])
+        out["traffic_bytes_per_launch"]["window_order"] = od["dram_read"] + od["dram_write"]
+        out["detail"]["window_order"] = od
+    json.dump(out, sys.stdout, indent=1)
     print()
 
 
