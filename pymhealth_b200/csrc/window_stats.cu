@@ -70,7 +70,8 @@ struct Partials {
     InT* mn;
     InT* mx;
     float* ll;     // line length inside + across the right edge
-    float* llb;    // ... the right-edge term alone
+    float* llb;    // ... line length WITHOUT the right-edge term (the last block of a window contributes this one: a
+                   //     subtraction "total - edge" would turn a NaN sample just past the window into NaN - NaN)
     float* zc;     // zero crossings inside + across the right edge (exact small integers)
     float* zcb;
 
@@ -431,9 +432,9 @@ __global__ void __launch_bounds__(kThreads, 3) window_stats_kernel(const StatsPl
             dst.mx[idx] = a.mx;
             if (TD) {
                 dst.ll[idx] = a.ll + llb;
-                dst.llb[idx] = llb;
+                dst.llb[idx] = a.ll;
                 dst.zc[idx] = a.zc + zcb;
-                dst.zcb[idx] = zcb;
+                dst.zcb[idx] = a.zc;
             }
         }
         __syncthreads();      // stage buffer fully consumed; cell partials visible
@@ -487,14 +488,14 @@ __global__ void __launch_bounds__(kThreads, 3) window_stats_kernel(const StatsPl
                     ring.s4[r] = v;
                 } else if (TD && grp == (M4 ? 3 : 2)) {
                     double u = 0;                    // float cell terms, float64 across cells
-                    for (int i = 0; i < g_cpb; ++i) u += static_cast<double>(cell.ll[c0 + i]);
-                    ring.ll[r] = static_cast<float>(u);
-                    ring.llb[r] = cell.llb[c0 + g_cpb - 1];
+                    for (int i = 0; i < g_cpb - 1; ++i) u += static_cast<double>(cell.ll[c0 + i]);
+                    ring.ll[r] = static_cast<float>(u + static_cast<double>(cell.ll[c0 + g_cpb - 1]));
+                    ring.llb[r] = static_cast<float>(u + static_cast<double>(cell.llb[c0 + g_cpb - 1]));
                 } else if (TD) {
                     float u = 0;
-                    for (int i = 0; i < g_cpb; ++i) u += cell.zc[c0 + i];
-                    ring.zc[r] = u;
-                    ring.zcb[r] = cell.zcb[c0 + g_cpb - 1];
+                    for (int i = 0; i < g_cpb - 1; ++i) u += cell.zc[c0 + i];
+                    ring.zc[r] = u + cell.zc[c0 + g_cpb - 1];
+                    ring.zcb[r] = u + cell.zcb[c0 + g_cpb - 1];
                 }
             }
             __syncthreads();
@@ -567,6 +568,8 @@ __global__ void __launch_bounds__(kThreads, 3) window_stats_kernel(const StatsPl
                     while (hi >= R1) hi -= R1;
                     direct = pre[(kNPre - 1) * R1 + hi] != pre[(kNPre - 1) * R1 + lo];      // a non-finite block inside
                 }
+                // LL / ZC: blocks 0 .. k-2 with their right edges, the last block without (that edge belongs to the next
+                // window only)
                 if (direct) {
                     S1 = ring.s1[r0];
                     S2 = ring.s2[r0];
@@ -574,21 +577,17 @@ __global__ void __launch_bounds__(kThreads, 3) window_stats_kernel(const StatsPl
                         S3 = ring.s3[r0];
                         S4 = ring.s4[r0];
                     }
-                    if (TD) {
-                        LL = ring.ll[r0];
-                        ZC = ring.zc[r0];
-                    }
                     for (int j = 1; j < g_k; ++j) {
+                        if (TD) {
+                            LL += ring.ll[r];
+                            ZC += ring.zc[r];
+                        }
                         r = wrap(r + 1, P.RB);
                         S1 += ring.s1[r];
                         S2 += ring.s2[r];
                         if (M4) {
                             S3 += ring.s3[r];
                             S4 += ring.s4[r];
-                        }
-                        if (TD) {
-                            LL += ring.ll[r];
-                            ZC += ring.zc[r];
                         }
                         mn = tmin<InT>(mn, ring.mn[r]);
                         mx = tmax<InT>(mx, ring.mx[r]);
@@ -601,8 +600,9 @@ __global__ void __launch_bounds__(kThreads, 3) window_stats_kernel(const StatsPl
                         S4 = pre[3 * R1 + hi] - pre[3 * R1 + lo];
                     }
                     if (TD) {
-                        LL = pre[(nq - 2) * R1 + hi] - pre[(nq - 2) * R1 + lo];
-                        ZC = pre[(nq - 1) * R1 + hi] - pre[(nq - 1) * R1 + lo];
+                        const int hi1 = hi > 0 ? hi - 1 : R1 - 1;
+                        LL = pre[(nq - 2) * R1 + hi1] - pre[(nq - 2) * R1 + lo];
+                        ZC = pre[(nq - 1) * R1 + hi1] - pre[(nq - 1) * R1 + lo];
                     }
                     for (int j = 1; j < g_k; ++j) {
                         r = wrap(r + 1, P.RB);
@@ -610,9 +610,9 @@ __global__ void __launch_bounds__(kThreads, 3) window_stats_kernel(const StatsPl
                         mx = tmax<InT>(mx, ring.mx[r]);
                     }
                 }
-                if (TD) {       // the right edge of the last block belongs to the next window only
-                    LL -= ring.llb[r];
-                    ZC -= ring.zcb[r];
+                if (TD) {
+                    LL += ring.llb[r];
+                    ZC += ring.zcb[r];
                 }
 
                 // shifted power sums -> central moments
