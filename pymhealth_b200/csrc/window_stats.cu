@@ -44,7 +44,7 @@ struct StatsPlan {
     const void* y;               // magnitude mode (accelerometer.py:198-225 fused into the staging copy): the series is
     const void* z;               // sqrt(x^2 + y^2 + z^2) of three arrays of the same geometry; null otherwise
     int64_t series_len, series_stride, total_elems;
-    int64_t nw, win_per_chunk;
+    int64_t nw, win_per_chunk, win_per_segment;
     int32_t chunks_per_series;
     int32_t W, S, g, k, hop, m, cpb, TB, RB, NS;
     int32_t flush;               // finalize once this many windows are pending
@@ -353,8 +353,15 @@ __global__ void __launch_bounds__(kThreads, 3) window_stats_kernel(const StatsPl
         }
         const InT* s = buf + d.lead;
         if (st == 0) {
-            c = static_cast<double>(ld(s, 0));
-            if (!isfinite(c)) c = 0.0;      // a NaN / inf first sample must not poison the whole chunk (any pivot is exact)
+            // pivot of the shifted power sums: the first sample of the chunk's SEGMENT (a fixed number of windows counted
+            // from the start of the series; a chunk is a power-of-two fraction of one), so that the sums -- and with
+            // them every bit of the table -- do not depend on how a call is cut into chunks, i.e. on how many series
+            // share the launch.  Any finite pivot is exact; a NaN / inf sample there must not poison the chunk.
+            const int64_t pidx = series_base + (w0 / P.win_per_segment) * P.win_per_segment * P.S;
+            if (P.y) c = static_cast<double>(magnitude3<InT>(xg[pidx], reinterpret_cast<const InT*>(P.y)[pidx],
+                                                             reinterpret_cast<const InT*>(P.z)[pidx]));
+            else c = static_cast<double>(xg[pidx]);
+            if (!isfinite(c)) c = 0.0;
         }
 
         // ---------------- phase 1: one cell per thread
@@ -862,10 +869,13 @@ int32_t window_stats_impl(const InT* x, const mhb_windows* geom, const int32_t* 
     const int64_t win_per_stage = P.TB / P.hop > 0 ? P.TB / P.hop : 1;
     const int64_t total_windows = nw * geom->n_series;
     const int64_t target_ctas = static_cast<int64_t>(kNumSMs) * 12;
-    int64_t wpc = (total_windows + target_ctas - 1) / target_ctas;
-    if (wpc < 8 * win_per_stage) wpc = 8 * win_per_stage;
-    if (wpc > 64 * win_per_stage) wpc = 64 * win_per_stage;
-    if (wpc > nw) wpc = nw;
+    // a chunk is segment / 2^j windows (segment = 64 stages): halve while the launch has too few CTAs
+    const int64_t seg = 64 * win_per_stage;
+    int64_t wpc = seg;
+    while (wpc % 2 == 0 && wpc / 2 >= 8 * win_per_stage && (wpc / 2) % win_per_stage == 0 &&
+           (total_windows + wpc - 1) / wpc < target_ctas)
+        wpc /= 2;
+    P.win_per_segment = seg;
     P.win_per_chunk = wpc;
     const int64_t cps = (nw + wpc - 1) / wpc;
     MHB_REQUIRE(cps * geom->n_series < (1LL << 31), MHB_E_UNSUPPORTED, "window_stats: too many chunks");

@@ -113,6 +113,12 @@ def window_table(x, wsize, wstep, features, zc_threshold=0.0, fs=1.0, out_dtype=
     elif tuple(out.shape) != (ns, nw, nf):
         raise ValueError("out has shape %s, expected %s" % (tuple(out.shape), (ns, nw, nf)))
     _check_out(torch, out, t)
+    if nw > 0 and ns > 0 and nf > 0 and t.device.index != torch.cuda.current_device():
+        with torch.cuda.device(t.device):          # launch on the device (and its current stream) that holds the series
+            res = window_table(t, wsize, wstep, features, zc_threshold=zc_threshold, fs=fs, out_dtype=out_dtype, out=out)
+        if was_numpy:
+            res = res.cpu().numpy()
+        return res[0] if was_1d else res
     if nw > 0 and ns > 0 and nf > 0:
         geom = L.MhbWindows(ns, n, t.stride(0) if ns > 1 else n, wsize, wstep)
         stream = _stream_ptr(torch)

@@ -139,3 +139,24 @@ def test_pipeline_host_buffers_float_and_raw_counts():
         np.testing.assert_array_equal(host_f, want)
         np.testing.assert_array_equal(host_c, want)
     assert pipe_f.launches_per_chunk() == 2
+
+
+def test_tables_do_not_depend_on_the_batch_composition():
+    """The rows of a series are the same bits whether it is processed alone or as one of many series (kernel 1a pivots sit
+    on fixed segments of the series, kernel 2 works on batches aligned to the series start): what makes the per-rank
+    tables of a sharded run identical to a single-GPU run whatever the shard sizes."""
+    import torch
+    from pymhealth_b200 import engine, synth, spectral as SP
+    from pymhealth_b200.generic import stats, timedom
+    dev = torch.device("cuda:0")
+    x = synth.device_accelerometer(8, 1_000_003, dev).view(24, -1)
+    sf = [stats.mean.feature(), stats.std.feature(), stats.var.feature(), stats.dmin.feature(), stats.dmax.feature(),
+          stats.skewness.feature(), stats.kurtosis.feature(), timedom.zero_crossing_count.feature(0.0), timedom.line_length.feature()]
+    pf = [r.feature() for r in _spectral_reducers()]
+    big = engine.window_table(x, 500, 250, sf + pf, fs=FS)
+    for rows in (slice(0, 1), slice(5, 8), slice(23, 24)):
+        alone = engine.window_table(x[rows].clone(), 500, 250, sf + pf, fs=FS)
+        assert torch.equal(alone, big[rows]), rows
+    if torch.cuda.device_count() >= 2:                     # ... and on another device of the box
+        other = engine.window_table(x[5:8].to("cuda:1"), 500, 250, sf + pf, fs=FS)
+        assert torch.equal(other.cpu(), big[5:8].cpu())
