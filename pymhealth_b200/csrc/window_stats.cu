@@ -22,6 +22,7 @@
 // Parity notes (SURVEY section 8c gotchas): population variance; kurtosis / skewness return 0 for a
 // constant window; zero is "not positive" for crossings; no partial tail window.
 #include <cstdlib>
+#include <math_constants.h>
 
 #include "common.cuh"
 
@@ -128,7 +129,20 @@ struct CellAcc {
     double s1 = 0, s2 = 0, s3 = 0, s4 = 0;
     float ll = 0.f, zc = 0.f;
     InT mn, mx;
+    bool nan = false;      // float64 cells: a NaN sample was met (DMNMX cannot propagate it; float32 uses FMNMX.NAN)
 };
+
+// per-sample extrema: float32 propagates NaN in the instruction itself; float64 takes the plain DMNMX and one
+// predicate-accumulating compare per sample, and the cell's extrema are set to NaN at its end
+__device__ __forceinline__ void accum_extrema(CellAcc<float>& a, float v) {
+    a.mn = tmin<float>(a.mn, v);
+    a.mx = tmax<float>(a.mx, v);
+}
+__device__ __forceinline__ void accum_extrema(CellAcc<double>& a, double v) {
+    a.mn = fmin(a.mn, v);
+    a.mx = fmax(a.mx, v);
+    a.nan = a.nan || (v != v);
+}
 
 template <typename InT, bool M4>
 __device__ __forceinline__ void accum_moments(CellAcc<InT>& a, InT v, double c) {
@@ -140,8 +154,7 @@ __device__ __forceinline__ void accum_moments(CellAcc<InT>& a, InT v, double c) 
         a.s3 = fma(d2, d, a.s3);
         a.s4 = fma(d2, d2, a.s4);
     }
-    a.mn = tmin<InT>(a.mn, v);
-    a.mx = tmax<InT>(a.mx, v);
+    accum_extrema(a, v);
 }
 
 // time-domain pair terms between neighbours (prev, v); pos flags are 1.0f / 0.0f
@@ -435,6 +448,7 @@ __global__ void __launch_bounds__(kThreads, 3) window_stats_kernel(const StatsPl
                 dst.s3[idx] = a.s3;
                 dst.s4[idx] = a.s4;
             }
+            if (sizeof(InT) == 8 && a.nan) a.mn = a.mx = static_cast<InT>(CUDART_NAN);
             dst.mn[idx] = a.mn;
             dst.mx[idx] = a.mx;
             if (TD) {
