@@ -57,13 +57,104 @@ __device__ __forceinline__ void warp_sort_regs(T* v, int lane) {
     }
 }
 
+// ---- float32 specialisation: sign-state network on GROUPS of lanes.
+// Measured on the B200 (tools/ubench/sort_pipes.cu, 8 warps per sub-partition): SHFL issues once every 4.0 cycles per
+// sub-partition (one warp shuffle per cycle and SM), FMNMX / FMUL once every ~1.0; the generic network above needs 1130
+// cycles per 256-element block and sub-partition.  Two changes:
+// (1) Sign states.  The generic network spends 2 instructions per cross-lane compare-exchange (FMNMX + predicated FMNMX)
+//     and 4 per in-register one whose direction depends on the lane (2 FMNMX + 2 FSEL).  Here every lane holds
+//     u = tau * v with a sign state tau = +-1:
+//       * in-register stages of a merge level whose direction is `down` for this lane: tau = -1, so the ascending
+//         compare-exchange (min to the lower index) of u IS the descending one of v -- no selects;
+//       * cross-lane stage: tau = +1 on lanes that keep the minimum and -1 on lanes that keep the maximum; partners
+//         then hold opposite states and  u = min(u, -shfl(u))  is  tau * (min or max of the two values): ONE FMNMX per
+//         element (the negation is an operand modifier).
+//     Changing tau is one FMUL by +-1 per element (exact).  Full warp, 8 elements per lane: 758 cycles per block.
+// (2) Fewer, longer lanes.  A block is sorted by a GROUP of GL lanes holding EPL = P2 / GL elements each (a warp sorts
+//     32 / GL blocks at once): the lane's own EPL elements are sorted by Batcher's odd-even merge network in registers
+//     (19 / 63 / 191 comparators for 8 / 16 / 32 elements), and only log2(GL) (log2(GL) + 1) / 2 merge stages cross lanes --
+//     GL = 8, EPL = 32: 48 shuffles per 256-element block instead of 120.
+// (-0.0 and +0.0 may come out in either order; they are equal as values.  NaN is outside the contract.)
+__device__ __forceinline__ void cex_f32(float& lo, float& hi) {     // ascending compare-exchange
+    const float a = lo, c = hi;
+    lo = fminf(a, c);
+    hi = fmaxf(a, c);
+}
+
+// Batcher's odd-even merge sort of u[LO .. LO + N), ascending, N = 2^m; template recursion, so that every index is a
+// compile-time constant and u[] stays in registers
+template <int LO, int N, int R>
+__device__ __forceinline__ void oem_merge_f32(float* u) {
+    if constexpr (2 * R < N) {
+        oem_merge_f32<LO, N, 2 * R>(u);
+        oem_merge_f32<LO + R, N, 2 * R>(u);
+#pragma unroll
+        for (int i = LO + R; i + R < LO + N; i += 2 * R) cex_f32(u[i], u[i + R]);
+    } else {
+        cex_f32(u[LO], u[LO + R]);
+    }
+}
+template <int LO, int N>
+__device__ __forceinline__ void oem_sort_f32(float* u) {
+    if constexpr (N > 1) {
+        oem_sort_f32<LO, N / 2>(u);
+        oem_sort_f32<LO + N / 2, N / 2>(u);
+        oem_merge_f32<LO, N, 1>(u);
+    }
+}
+template <int N>
+__device__ __forceinline__ void lane_sort_f32(float* u) { oem_sort_f32<0, N>(u); }
+
+// Sorts the GL * EPL elements held by each aligned group of GL lanes (element e = l * EPL + i on lane l of the group,
+// i = 0 .. EPL - 1) ascending.  l = lane % GL.  The input may be in any order (any element-to-lane mapping).
+template <int EPL, int GL>
+__device__ __forceinline__ void group_sort_regs_f32(float* u, int l) {
+    bool neg = false;                                   // tau == -1
+    auto flip = [&](bool req) {
+        const float s = (req != neg) ? -1.0f : 1.0f;
+#pragma unroll
+        for (int i = 0; i < EPL; ++i) u[i] = __fmul_rn(u[i], s);
+        neg = req;
+    };
+    // merge levels up to EPL: the lane's own elements, descending on odd lanes (as level EPL of the bitonic scheme wants)
+    if (GL > 1) flip((l & 1) != 0);
+    lane_sort_f32<EPL>(u);
+#pragma unroll
+    for (int k2 = 2 * EPL; k2 <= GL * EPL; k2 <<= 1) {
+        const bool dn = k2 < GL * EPL ? (l & (k2 / EPL)) != 0 : false;     // direction of this merge level for the lane
+#pragma unroll
+        for (int j = k2 >> 1; j >= EPL; j >>= 1) {
+            const int mask = j / EPL;
+            const bool upper = (l & mask) != 0;
+            flip(dn != upper);                          // keep-min lanes +1, keep-max lanes -1
+#pragma unroll
+            for (int i = 0; i < EPL; ++i) u[i] = fminf(u[i], -__shfl_xor_sync(0xffffffffu, u[i], mask));
+        }
+        flip(dn);
+#pragma unroll
+        for (int j = EPL >> 1; j > 0; j >>= 1)
+#pragma unroll
+            for (int i = 0; i < EPL; ++i)
+                if ((i ^ j) > i) cex_f32(u[i], u[i ^ j]);
+    }
+    flip(false);
+}
+
+template <int EPL>
+__device__ __forceinline__ void warp_sort_regs_f32(float* u, int lane) { group_sort_regs_f32<EPL, 32>(u, lane); }
+
+template <int EPL>
+__device__ __forceinline__ void warp_sort_regs_dispatch(float* v, int lane) { warp_sort_regs_f32<EPL>(v, lane); }
+template <int EPL>
+__device__ __forceinline__ void warp_sort_regs_dispatch(double* v, int lane) { warp_sort_regs<double, EPL>(v, lane); }
+
 // sort the p2 = 32 * EPL elements of buf[] (shared memory, already padded) in place
 template <typename T, int EPL>
 __device__ __forceinline__ void sort_smem_via_regs(T* __restrict__ buf, int lane) {
     T v[EPL];
 #pragma unroll
     for (int i = 0; i < EPL; ++i) v[i] = buf[lane * EPL + i];
-    warp_sort_regs<T, EPL>(v, lane);
+    warp_sort_regs_dispatch<EPL>(v, lane);
 #pragma unroll
     for (int i = 0; i < EPL; ++i) buf[lane * EPL + i] = v[i];
 }

@@ -22,6 +22,10 @@
 namespace mhb {
 
 // window_order_blocks.cu: sort every block once + k-way selection (order statistics only); -100 = not covered
+// window_order_stream.cu: float32, W = g or 2 g with S = g (warp-private streaming, no block barrier)
+int32_t window_order_stream_try(const float* x, const mhb_windows* geom, int64_t nw, const int32_t* h_features,
+                                const double* h_params, int32_t n_features, const mhb_table* table, void* stream_v);
+
 template <typename InT>
 int32_t window_order_blocks_try(const InT* x, const mhb_windows* geom, int64_t nw, const int32_t* h_features,
                                 const double* h_params, int32_t n_features, const mhb_table* table, void* stream_v);
@@ -270,6 +274,12 @@ int32_t window_order_impl(const InT* x, const mhb_windows* geom, const int32_t* 
             MHB_REQUIRE(geom->wsize >= 2, MHB_E_ARG, "window_order: Hjorth features need wsize >= 2");
         } else {
             P.need_sort = 1;
+        }
+    }
+    if constexpr (sizeof(InT) == 4) {
+        if (getenv("MHB_ORDER_FULLSORT") == nullptr && getenv("MHB_ORDER_NOSTREAM") == nullptr) {
+            const int32_t st = window_order_stream_try(x, geom, nw, h_features, h_params, n_features, table, stream_v);
+            if (st != -100) return st;
         }
     }
     if (getenv("MHB_ORDER_FULLSORT") == nullptr) {

@@ -141,21 +141,12 @@ __device__ __forceinline__ void merge_pair(const T* __restrict__ A, const T* __r
     if (upper == inf) upper = lower;            // r is the top rank
 }
 
-// MERGE: k <= 2 (merge-path selection, a thread per window and column); otherwise k-way bisection (a warp per window)
-template <typename T, int EPL>
-__device__ __forceinline__ void sort_block_regs(const T* __restrict__ src, T* __restrict__ dst, int g, int lane) {
-    T v[EPL];
-#pragma unroll
-    for (int i = 0; i < EPL; ++i) {
-        const int e = lane * EPL + i;
-        v[i] = e < g ? src[e] : Key<T>::inf();
-    }
-    warp_sort_regs<T, EPL>(v, lane);
-#pragma unroll
-    for (int i = 0; i < EPL; ++i) dst[lane * EPL + i] = v[i];
-}
-
-template <typename InT, typename OutT, bool MERGE>
+// MERGE: k <= 2 (merge-path selection, a thread per window and column); otherwise k-way bisection (a warp per window).
+// EPL > 0: blocks of <= 32 * EPL samples are sorted in registers (sort_regs.cuh), one warp per block; the samples of
+// the warp's NEXT block (of this batch, or its first one of the CTA's next batch -- registers do not depend on the
+// shared-memory barriers) are loaded before the current one is sorted, so the ~1 us of an HBM load is never exposed.
+// EPL == 0: larger blocks, bitonic network in shared memory.
+template <typename InT, typename OutT, bool MERGE, int EPL>
 __global__ void __launch_bounds__(kThreadsOB, 4) window_order_blocks_kernel(const BlocksPlan P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     InT* sorted = reinterpret_cast<InT*>(smem_raw);                      // [NB][P2g + 1]
@@ -163,47 +154,85 @@ __global__ void __launch_bounds__(kThreadsOB, 4) window_order_blocks_kernel(cons
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int P2 = P.P2g, g = P.g, n = P.W;
     const int BS = P2 + 1;       // block stride: odd, so that lanes probing the same position of different blocks do not collide
+    constexpr int NR = EPL > 0 ? EPL : 1;
+
+    auto batch_geom = [&](int64_t b, int64_t& series, int64_t& w0, int& nwin, int& nblk, const InT*& src0) {
+        series = b / P.batches_per_series;
+        const int64_t bi = b - series * P.batches_per_series;
+        w0 = bi * P.nwb;
+        const int64_t left = P.nw - w0;
+        nwin = left < P.nwb ? static_cast<int>(left) : P.nwb;
+        nblk = (nwin - 1) * P.hop + P.k;
+        src0 = xg + series * P.series_stride + w0 * P.hop * static_cast<int64_t>(g);
+    };
+    auto load_block = [&](InT* v, const InT* src) {
+#pragma unroll
+        for (int i = 0; i < NR; ++i) {
+            const int e = lane * NR + i;
+            v[i] = e < g ? src[e] : Key<InT>::inf();
+        }
+    };
+    InT nxt[NR];
+    if (EPL > 0 && blockIdx.x < P.total_batches) {
+        int64_t series, w0;
+        int nwin, nblk;
+        const InT* src0;
+        batch_geom(blockIdx.x, series, w0, nwin, nblk, src0);
+        if (warp < nblk) load_block(nxt, src0 + static_cast<int64_t>(warp) * g);
+    }
 
     for (int64_t b = blockIdx.x; b < P.total_batches; b += gridDim.x) {
-        const int64_t series = b / P.batches_per_series;
-        const int64_t bi = b - series * P.batches_per_series;
-        const int64_t w0 = bi * P.nwb;
-        const int64_t left = P.nw - w0;
-        const int nwin = left < P.nwb ? static_cast<int>(left) : P.nwb;
-        const int nblk = (nwin - 1) * P.hop + P.k;
-        const InT* src0 = xg + series * P.series_stride + w0 * P.hop * static_cast<int64_t>(g);
+        int64_t series, w0;
+        int nwin, nblk;
+        const InT* src0;
+        batch_geom(b, series, w0, nwin, nblk, src0);
         __syncthreads();                                                  // previous batch's selections are done
         // ---- phase 1: stage and sort every block of the batch, one warp per block
         for (int blk = warp; blk < nblk; blk += kWarpsOB) {
             InT* buf = sorted + static_cast<size_t>(blk) * BS;
             const InT* src = src0 + static_cast<int64_t>(blk) * g;
-            if (P2 <= 512) {                       // register-resident network (<= 16 elements per lane)
-                switch (P2) {
-                    case 32: sort_block_regs<InT, 1>(src, buf, g, lane); break;
-                    case 64: sort_block_regs<InT, 2>(src, buf, g, lane); break;
-                    case 128: sort_block_regs<InT, 4>(src, buf, g, lane); break;
-                    case 256: sort_block_regs<InT, 8>(src, buf, g, lane); break;
-                    default: sort_block_regs<InT, 16>(src, buf, g, lane); break;
+            if constexpr (EPL > 0) {               // register-resident network (<= 16 elements per lane)
+                InT v[NR];
+#pragma unroll
+                for (int i = 0; i < NR; ++i) v[i] = nxt[i];
+                if (blk + kWarpsOB < nblk) {
+                    load_block(nxt, src + static_cast<int64_t>(kWarpsOB) * g);
+                } else if (b + gridDim.x < P.total_batches) {
+                    int64_t series2, w02;
+                    int nwin2, nblk2;
+                    const InT* src2;
+                    batch_geom(b + gridDim.x, series2, w02, nwin2, nblk2, src2);
+                    if (warp < nblk2) load_block(nxt, src2 + static_cast<int64_t>(warp) * g);
                 }
-                continue;
-            }
-            for (int i = lane; i < P2; i += 32) buf[i] = i < g ? src[i] : Key<InT>::inf();
-            __syncwarp();
-            for (int k2 = 2; k2 <= P2; k2 <<= 1) {
-                for (int j = k2 >> 1; j > 0; j >>= 1) {
-                    for (int t = lane; t < (P2 >> 1); t += 32) {
-                        const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
-                        const int l = i + j;
-                        const InT a = buf[i], c = buf[l];
-                        const bool up = (i & k2) == 0;
-                        if ((a > c) == up) {
-                            buf[i] = c;
-                            buf[l] = a;
+                warp_sort_regs_dispatch<NR>(v, lane);
+#pragma unroll
+                for (int i = 0; i < NR; ++i) buf[lane * NR + i] = v[i];
+            } else {
+                for (int i = lane; i < P2; i += 32) buf[i] = i < g ? src[i] : Key<InT>::inf();
+                __syncwarp();
+                for (int k2 = 2; k2 <= P2; k2 <<= 1) {
+                    for (int j = k2 >> 1; j > 0; j >>= 1) {
+                        for (int t = lane; t < (P2 >> 1); t += 32) {
+                            const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                            const int l = i + j;
+                            const InT a = buf[i], c = buf[l];
+                            const bool up = (i & k2) == 0;
+                            if ((a > c) == up) {
+                                buf[i] = c;
+                                buf[l] = a;
+                            }
                         }
+                        __syncwarp();
                     }
-                    __syncwarp();
                 }
             }
+        }
+        if (EPL > 0 && warp >= nblk && b + gridDim.x < P.total_batches) {     // a warp without a block in a short batch
+            int64_t series2, w02;
+            int nwin2, nblk2;
+            const InT* src2;
+            batch_geom(b + gridDim.x, series2, w02, nwin2, nblk2, src2);
+            if (warp < nblk2) load_block(nxt, src2 + static_cast<int64_t>(warp) * g);
         }
         __syncthreads();
         // ---- phase 2: order statistics of every window of the batch
@@ -365,17 +394,27 @@ int32_t window_order_blocks_try(const InT* x, const mhb_windows* geom, int64_t n
     int64_t ctas = static_cast<int64_t>(kNumSMs) * 4;
     if (ctas > P.total_batches) ctas = P.total_batches;
     cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
-#define MHB_GOB(OUT)                                                                                          \
+#define MHB_GOB_E(OUT, E_)                                                                                    \
     {                                                                                                         \
-        auto kern = P.k <= 2 ? window_order_blocks_kernel<InT, OUT, true>                                     \
-                             : window_order_blocks_kernel<InT, OUT, false>;                                   \
+        auto kern = P.k <= 2 ? window_order_blocks_kernel<InT, OUT, true, E_>                                 \
+                             : window_order_blocks_kernel<InT, OUT, false, E_>;                               \
         e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));  \
         if (e == cudaSuccess) {                                                                               \
             kern<<<static_cast<unsigned>(ctas), kThreadsOB, smem, stream>>>(P);                               \
             e = cudaGetLastError();                                                                           \
         }                                                                                                     \
     }
+#define MHB_GOB(OUT)                                                                                          \
+    switch (p2) {                                                                                             \
+        case 32: MHB_GOB_E(OUT, 1) break;                                                                     \
+        case 64: MHB_GOB_E(OUT, 2) break;                                                                     \
+        case 128: MHB_GOB_E(OUT, 4) break;                                                                    \
+        case 256: MHB_GOB_E(OUT, 8) break;                                                                    \
+        case 512: MHB_GOB_E(OUT, 16) break;                                                                   \
+        default: MHB_GOB_E(OUT, 0) break;                                                                     \
+    }
     if (table->out_f32) MHB_GOB(float) else MHB_GOB(double)
+#undef MHB_GOB_E
 #undef MHB_GOB
     return cuda_status(e, "window_order_blocks launch");
 }
