@@ -80,35 +80,87 @@ __device__ __forceinline__ void cex_f32(float& lo, float& hi) {     // ascending
     lo = fminf(a, c);
     hi = fmaxf(a, c);
 }
+// The same with the maximum formed on the FMA pipe: bits(max) = bits(a) + bits(c) - bits(min) (exact: the minimum IS one
+// of the two bit patterns), as two IMADs whose multipliers +1 / -1 are RUNTIME values (`one`; with a literal ptxas folds
+// them into one IADD3, which is the ALU pipe again).  FMNMX issues once every 2 cycles per sub-partition (ALU pipe, 16
+// lanes), IMAD likewise on the heavy FMA pipe: a network that uses this form for one compare-exchange out of three
+// measured best (630 -> 595 cycles per 256-element block; two out of three: 614; tools/ubench/sort_pipes.cu).
+__device__ __forceinline__ void cex_f32_fma(float& lo, float& hi, int one) {
+    const float a = lo, c = hi;
+    const float mn = fminf(a, c);
+    int t, m;
+    asm("mad.lo.s32 %0, %1, %2, %3;" : "=r"(t) : "r"(__float_as_int(a)), "r"(one), "r"(__float_as_int(c)));
+    asm("mad.lo.s32 %0, %1, %2, %3;" : "=r"(m) : "r"(__float_as_int(mn)), "r"(-one), "r"(t));
+    lo = mn;
+    hi = __int_as_float(m);
+}
+template <int SEL>
+__device__ __forceinline__ void cex_mix(float& lo, float& hi, int one) {
+#ifndef MHB_CEX_FMA_OF
+#define MHB_CEX_FMA_OF 3          // share of FMA-pipe compare-exchanges: MHB_CEX_FMA_N out of MHB_CEX_FMA_OF
+#define MHB_CEX_FMA_N 1
+#endif
+    if constexpr (SEL % MHB_CEX_FMA_OF >= MHB_CEX_FMA_N) cex_f32(lo, hi);
+    else cex_f32_fma(lo, hi, one);
+}
+
+// compare-exchanges (i, i + R) for i = I0, I0 + 2 R, ... while i + R < END
+template <int I0, int END, int R, bool MIX>
+__device__ __forceinline__ void oem_row_f32(float* u, int one) {
+    if constexpr (I0 + R < END) {
+        if constexpr (MIX) cex_mix<I0 / R>(u[I0], u[I0 + R], one);
+        else cex_f32(u[I0], u[I0 + R]);
+        oem_row_f32<I0 + 2 * R, END, R, MIX>(u, one);
+    }
+}
 
 // Batcher's odd-even merge sort of u[LO .. LO + N), ascending, N = 2^m; template recursion, so that every index is a
-// compile-time constant and u[] stays in registers
-template <int LO, int N, int R>
-__device__ __forceinline__ void oem_merge_f32(float* u) {
+// compile-time constant and u[] stays in registers.  `one` == 1 at run time (see cex_f32_fma); one == 0 selects the
+// plain compare-exchanges everywhere.
+template <int LO, int N, int R, bool MIX>
+__device__ __forceinline__ void oem_merge_f32(float* u, int one) {
     if constexpr (2 * R < N) {
-        oem_merge_f32<LO, N, 2 * R>(u);
-        oem_merge_f32<LO + R, N, 2 * R>(u);
-#pragma unroll
-        for (int i = LO + R; i + R < LO + N; i += 2 * R) cex_f32(u[i], u[i + R]);
+        oem_merge_f32<LO, N, 2 * R, MIX>(u, one);
+        oem_merge_f32<LO + R, N, 2 * R, MIX>(u, one);
+        oem_row_f32<LO + R, LO + N, R, MIX>(u, one);
     } else {
-        cex_f32(u[LO], u[LO + R]);
+        if constexpr (MIX) cex_mix<(LO + R) / 1 + 1>(u[LO], u[LO + R], one);
+        else cex_f32(u[LO], u[LO + R]);
     }
 }
-template <int LO, int N>
-__device__ __forceinline__ void oem_sort_f32(float* u) {
+template <int LO, int N, bool MIX>
+__device__ __forceinline__ void oem_sort_f32(float* u, int one) {
     if constexpr (N > 1) {
-        oem_sort_f32<LO, N / 2>(u);
-        oem_sort_f32<LO + N / 2, N / 2>(u);
-        oem_merge_f32<LO, N, 1>(u);
+        oem_sort_f32<LO, N / 2, MIX>(u, one);
+        oem_sort_f32<LO + N / 2, N / 2, MIX>(u, one);
+        oem_merge_f32<LO, N, 1, MIX>(u, one);
     }
 }
-template <int N>
-__device__ __forceinline__ void lane_sort_f32(float* u) { oem_sort_f32<0, N>(u); }
+template <int N, bool MIX>
+__device__ __forceinline__ void lane_sort_f32(float* u, int one) { oem_sort_f32<0, N, MIX>(u, one); }
 
 // Sorts the GL * EPL elements held by each aligned group of GL lanes (element e = l * EPL + i on lane l of the group,
 // i = 0 .. EPL - 1) ascending.  l = lane % GL.  The input may be in any order (any element-to-lane mapping).
-template <int EPL, int GL>
-__device__ __forceinline__ void group_sort_regs_f32(float* u, int l) {
+template <int J, int I, int EPL, bool MIX>
+__device__ __forceinline__ void merge_stage_f32(float* u, int one) {      // in-register bitonic merge stage, distance J
+    if constexpr (I < EPL) {
+        if constexpr ((I ^ J) > I) {
+            if constexpr (MIX) cex_mix<I + J>(u[I], u[I ^ J], one);
+            else cex_f32(u[I], u[I ^ J]);
+        }
+        merge_stage_f32<J, I + 1, EPL, MIX>(u, one);
+    }
+}
+template <int J, int EPL, bool MIX>
+__device__ __forceinline__ void merge_stages_f32(float* u, int one) {
+    if constexpr (J > 0) {
+        merge_stage_f32<J, 0, EPL, MIX>(u, one);
+        merge_stages_f32<J / 2, EPL, MIX>(u, one);
+    }
+}
+
+template <int EPL, int GL, bool MIX = false>
+__device__ __forceinline__ void group_sort_regs_f32(float* u, int l, int one = 0) {
     bool neg = false;                                   // tau == -1
     auto flip = [&](bool req) {
         const float s = (req != neg) ? -1.0f : 1.0f;
@@ -118,7 +170,7 @@ __device__ __forceinline__ void group_sort_regs_f32(float* u, int l) {
     };
     // merge levels up to EPL: the lane's own elements, descending on odd lanes (as level EPL of the bitonic scheme wants)
     if (GL > 1) flip((l & 1) != 0);
-    lane_sort_f32<EPL>(u);
+    lane_sort_f32<EPL, MIX>(u, one);
 #pragma unroll
     for (int k2 = 2 * EPL; k2 <= GL * EPL; k2 <<= 1) {
         const bool dn = k2 < GL * EPL ? (l & (k2 / EPL)) != 0 : false;     // direction of this merge level for the lane
@@ -131,11 +183,7 @@ __device__ __forceinline__ void group_sort_regs_f32(float* u, int l) {
             for (int i = 0; i < EPL; ++i) u[i] = fminf(u[i], -__shfl_xor_sync(0xffffffffu, u[i], mask));
         }
         flip(dn);
-#pragma unroll
-        for (int j = EPL >> 1; j > 0; j >>= 1)
-#pragma unroll
-            for (int i = 0; i < EPL; ++i)
-                if ((i ^ j) > i) cex_f32(u[i], u[i ^ j]);
+        merge_stages_f32<EPL / 2, EPL, MIX>(u, one);
     }
     flip(false);
 }

@@ -48,6 +48,7 @@ struct StreamPlan {
     int64_t series_stride, nw, chunks_per_series, total_chunks;
     int32_t g, k, n, cw;                 // block length, blocks per window (1 | 2), window length, windows per chunk
     int32_t slot_stride;                 // floats per ring slot
+    int32_t one;                         // == 1: opaque multiplier of the FMA-pipe compare-exchange (sort_regs.cuh)
     void* out;
     int64_t o_series, o_window, o_col;
     int32_t n_features;
@@ -94,7 +95,7 @@ __global__ void __launch_bounds__(kThreadsOS, 4) window_order_stream_kernel(cons
                 const float* nx = src0 + static_cast<int64_t>(b0 + kNG) * g + lane * 32;
                 asm volatile("prefetch.global.L2 [%0];" ::"l"(nx));
             }
-            group_sort_regs_f32<EPL, kGL>(u, l);
+            group_sort_regs_f32<EPL, kGL, true>(u, l, P.one);
             float* slot = ring + (blk % kRing) * P.slot_stride;
             if (have) {
 #pragma unroll
@@ -185,6 +186,7 @@ int32_t window_order_stream_try(const float* x, const mhb_windows* geom, int64_t
     int slot = static_cast<int>(p2 + p2 / 32);
     while (slot % 32 != 8) ++slot;                      // the 4 groups' rows start 8 banks apart
     P.slot_stride = slot;
+    P.one = 1;
     P.out = table->out;
     P.o_series = table->series_stride;
     P.o_window = table->window_stride;

@@ -11,7 +11,7 @@
 using namespace mhb;
 
 // grouped sort: GL lanes x EPL elements per 256-element block, 32 / GL blocks per warp
-template <int EPL, int GL>
+template <int EPL, int GL, bool MIX>
 __global__ void __launch_bounds__(256, 4) kg(float* out, int n_iter, float s) {
     float v[EPL];
     const int lane = threadIdx.x & 31;
@@ -19,7 +19,7 @@ __global__ void __launch_bounds__(256, 4) kg(float* out, int n_iter, float s) {
     for (int i = 0; i < EPL; ++i) v[i] = __sinf(threadIdx.x * 0.37f + i * 1.1f + blockIdx.x);
 #pragma unroll 1
     for (int it = 0; it < n_iter; ++it) {
-        group_sort_regs_f32<EPL, GL>(v, lane % GL);
+        group_sort_regs_f32<EPL, GL, MIX>(v, lane % GL, static_cast<int>(s));
 #pragma unroll
         for (int i = 0; i < EPL; ++i) v[i] = v[i] * s + (float)((lane * 7 + i * 13 + it) & 31);
     }
@@ -29,16 +29,16 @@ __global__ void __launch_bounds__(256, 4) kg(float* out, int n_iter, float s) {
     out[blockIdx.x * blockDim.x + threadIdx.x] = acc;
 }
 
-template <int EPL, int GL>
+template <int EPL, int GL, bool MIX = false>
 void run_g(const char* name, float* out, int n_iter) {
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0);
     cudaEventCreate(&e1);
     const int ctas = 148 * 4;
-    kg<EPL, GL><<<ctas, 256>>>(out, 16, 1.0f);
+    kg<EPL, GL, MIX><<<ctas, 256>>>(out, 16, 1.0f);
     cudaDeviceSynchronize();
     cudaEventRecord(e0);
-    kg<EPL, GL><<<ctas, 256>>>(out, n_iter, 1.0f);
+    kg<EPL, GL, MIX><<<ctas, 256>>>(out, n_iter, 1.0f);
     cudaEventRecord(e1);
     cudaDeviceSynchronize();
     float ms = 0;
@@ -86,6 +86,22 @@ __global__ void __launch_bounds__(256, 4) k(float* out, int n_iter, float s) {
             for (int u = 0; u < 16; ++u)
 #pragma unroll
                 for (int i = 0; i < 8; ++i) v[i] = fminf(__fmul_rn(v[i], s), -__shfl_xor_sync(0xffffffffu, __fmul_rn(v[i], s), 1 + (u & 15)));
+        } else if (MODE == 7) {
+            // compare-exchange with the maximum formed on the FMA pipe: bits(max) = bits(a) + bits(c) - bits(min), two IMADs
+            // whose multipliers (+1, -1) are runtime values (a literal folds into one IADD3 -- ALU pipe again)
+            const int one = __float_as_int(s) >> 23 == 127 ? 1 : 2, mone = -one;
+#pragma unroll
+            for (int u = 0; u < 16; ++u)
+#pragma unroll
+                for (int i = 0; i < 8; i += 2) {
+                    const float a = v[i], c = v[i ^ 1 ^ (u & 6)];
+                    const float mn = fminf(a, c);
+                    int t, m;
+                    asm("mad.lo.s32 %0, %1, %2, %3;" : "=r"(t) : "r"(__float_as_int(a)), "r"(one), "r"(__float_as_int(c)));
+                    asm("mad.lo.s32 %0, %1, %2, %3;" : "=r"(m) : "r"(__float_as_int(mn)), "r"(mone), "r"(t));
+                    v[i] = mn;
+                    v[i ^ 1 ^ (u & 6)] = __int_as_float(m);
+                }
         } else if (MODE == 6) {
 #pragma unroll
             for (int u = 0; u < 16; ++u)
@@ -133,6 +149,7 @@ int main() {
     run<0>("generic bitonic sort (256 elements / warp)", 0, out, n);
     run<1>("sign-state sort (256 elements / warp)", 0, out, n);
     run_g<32, 8>("group sort 8 lanes x 32 (4 blocks / warp)", out, n / 4);
+    run_g<32, 8, true>("group sort 8 lanes x 32, 1/3 FMA-pipe maxima", out, n / 4);
     run_g<16, 16>("group sort 16 lanes x 16 (2 blocks / warp)", out, n / 2);
     run_g<8, 32>("group sort 32 lanes x 8", out, n);
     run_g<8, 8>("group sort 8 lanes x 8 (64-element blocks)", out, n);
@@ -142,6 +159,7 @@ int main() {
     run<4>("FMUL x128", 128, out, n);
     run<5>("FMUL+FMUL+SHFL+FMNMX x128", 512, out, n);
     run<6>("in-register compare-exchange x64", 128, out, n);
+    run<7>("compare-exchange FMNMX + 2 IMAD x64", 192, out, n);
     printf("cudaGetLastError: %s\n", cudaGetErrorString(cudaGetLastError()));
     return 0;
 }
