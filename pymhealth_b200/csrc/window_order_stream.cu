@@ -86,11 +86,10 @@ __global__ void __launch_bounds__(kThreadsOS, 4) window_order_stream_kernel(cons
             // ---- load (any element-to-lane mapping will do: 8 lanes read 32 contiguous bytes) and sort
             float u[EPL];
             const float* src = src0 + static_cast<int64_t>(blk) * g;
+            const float* srcl = src + l;
+            const int nfull = have ? (g - l + kGL - 1) / kGL : 0;       // elements of this lane: i < nfull
 #pragma unroll
-            for (int i = 0; i < EPL; ++i) {
-                const int e = i * kGL + l;
-                u[i] = (have && e < g) ? __ldg(src + e) : inf;
-            }
+            for (int i = 0; i < EPL; ++i) u[i] = i < nfull ? __ldg(srcl + i * kGL) : inf;
             if ((b0 + kNG) * g + lane * 32 < nblk * g && lane * 32 < kNG * g) {      // next iteration's samples -> L2 while this one sorts
                 const float* nx = src0 + static_cast<int64_t>(b0 + kNG) * g + lane * 32;
                 asm volatile("prefetch.global.L2 [%0];" ::"l"(nx));
@@ -98,8 +97,14 @@ __global__ void __launch_bounds__(kThreadsOS, 4) window_order_stream_kernel(cons
             group_sort_regs_f32<EPL, kGL, true>(u, l, P.one);
             float* slot = ring + (blk % kRing) * P.slot_stride;
             if (have) {
+                if constexpr (EPL == 32) {               // pos_of(32 l + i) = 33 l + i: one base, immediate offsets
+                    float* row = slot + l * 33;
 #pragma unroll
-                for (int i = 0; i < EPL; ++i) slot[pos_of(l * EPL + i)] = u[i];
+                    for (int i = 0; i < EPL; ++i) row[i] = u[i];
+                } else {
+#pragma unroll
+                    for (int i = 0; i < EPL; ++i) slot[pos_of(l * EPL + i)] = u[i];
+                }
             }
             __syncwarp();
             // ---- selection: group gi owns the window that ENDS with its block

@@ -92,3 +92,46 @@ def test_percentile_next_to_100(W, S):
     assert np.all(np.isfinite(hi)) and np.all(np.isfinite(lo))
     np.testing.assert_allclose(hi, mx, rtol=1e-12)
     np.testing.assert_allclose(lo, mn, rtol=1e-12, atol=1e-300)
+
+
+# ---- the streaming kernel (window_order_stream.cu): float32, W = g or 2 g with S = g, only median / percentile / IQR in
+# the call -- every lane-group size (g <= 32, 64, 128, 256), odd block lengths, chunk boundaries (127 / 128 windows per
+# warp chunk), tiny series, several series of one launch
+@pytest.mark.parametrize("n,W,S", [(40_000, 500, 250), (64_250, 250, 250), (9_000, 64, 32), (7_001, 96, 48), (30_011, 200, 100),
+                                   (5_000, 34, 17), (70_000, 512, 256), (2_600, 32, 16), (3_333, 33, 33), (500, 500, 250),
+                                   (750, 500, 250), (1_249, 500, 250), (32_500, 500, 250), (32_750, 500, 250)])
+def test_stream_kernel_vs_oracle(n, W, S):
+    from oracle import windows as OW
+    from pymhealth_b200 import engine
+    from pymhealth_b200.generic import stats
+    rng = np.random.default_rng(n * 7 + W)
+    x = np.round(rng.standard_normal((3, n)) * 40).astype(np.float32) / 16      # many ties
+    x[1] = rng.standard_normal(n).astype(np.float32) * 1e-3 + 1.0
+    x[2, ::7] = -x[2, ::7]
+    feats = [stats.median.feature(), stats.percentile.feature(0.0), stats.percentile.feature(100.0),
+             stats.percentile.feature(37.5), stats.percentile.feature(99.99), stats.interquartile_range.feature(),
+             stats.percentile.feature(90.0)]
+    got = engine.window_table(x, W, S, feats)                       # numpy in -> float64 table [3, nw, 7]
+    names = [("median", None), ("percentile", 0.0), ("percentile", 100.0), ("percentile", 37.5), ("percentile", 99.99),
+             ("iqr", None), ("percentile", 90.0)]
+    for s in range(3):
+        for j, (nme, q) in enumerate(names):
+            want = OW.rolling(nme, x[s], W, S, q)
+            assert got[s, :, j].shape == want.shape
+            if j < 3:           # selected samples (the even-length median is an exact float64 mean of two float32 values)
+                np.testing.assert_array_equal(got[s, :, j], want, err_msg="%s q=%s series %d" % (nme, q, s))
+            else:
+                np.testing.assert_allclose(got[s, :, j], want, rtol=1e-13, atol=1e-300, err_msg="%s q=%s series %d" % (nme, q, s))
+
+
+def test_stream_kernel_matches_batch_kernel(monkeypatch):
+    """Same table, bit for bit, as the batch kernel it replaced on this geometry (window_order_blocks.cu)."""
+    from pymhealth_b200 import engine, synth
+    from pymhealth_b200.generic import stats
+    x = synth.accelerometer(3, 400_000)
+    feats = [stats.median.feature(), stats.percentile.feature(90.0), stats.interquartile_range.feature()]
+    a = engine.window_table(x, 500, 250, feats)
+    monkeypatch.setenv("MHB_ORDER_NOSTREAM", "1")
+    b = engine.window_table(x, 500, 250, feats)
+    np.testing.assert_allclose(a, b, rtol=1e-15, atol=0)
+    np.testing.assert_array_equal(a[:, :, 0], b[:, :, 0])
