@@ -59,26 +59,30 @@ def feature_list():
     return stream, spec
 
 
-def lib_sha256():
+def csrc_sha256():
+    """sha256 over the CUDA sources the library is built from (sorted csrc/*.cu, *.cuh, Makefile).  A hash of the
+    binary would not do: nvcc's anonymous-namespace symbol names differ from build to build."""
+    import glob
     import hashlib
-    p = os.path.join(ROOT, "pymhealth_b200", "libmhb200.so")
-    try:
-        return hashlib.sha256(open(p, "rb").read()).hexdigest()
-    except Exception:
-        return None
+    d = os.path.join(ROOT, "pymhealth_b200", "csrc")
+    h = hashlib.sha256()
+    for f in sorted(glob.glob(os.path.join(d, "*.cu")) + glob.glob(os.path.join(d, "*.cuh")) + [os.path.join(d, "Makefile")]):
+        h.update(os.path.basename(f).encode())
+        h.update(open(f, "rb").read())
+    return h.hexdigest()
 
 
 def ncu_traffic(nsub):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures of the bench
     launches (profiles/ncu_traffic.json, written by tools/ncu_traffic.py from the .ncu-rep files).  The file names the
-    sha256 of the libmhb200.so it was taken from and the shard size: a capture of another build or another size is NOT
+    sha256 of the kernel sources it was taken from and the shard size: a capture of other sources or another size is NOT
     used (traffic = null) -- a kernel change cannot inherit the old figure silently."""
     p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     try:
         d = json.load(open(p))
     except Exception:
         return {}
-    if int(d.get("subjects_per_gpu", -1)) != int(nsub) or d.get("lib_sha256") != lib_sha256():
+    if int(d.get("subjects_per_gpu", -1)) != int(nsub) or d.get("csrc_sha256") != csrc_sha256():
         return {}
     return {k: v for k, v in d.get("traffic_bytes_per_launch", {}).items()}
 

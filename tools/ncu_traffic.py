@@ -1,7 +1,8 @@
 #!/usr/bin/env python3
 """Extract per-launch DRAM traffic of the bench kernels from `ncu --set full` reports taken at bench shard size.
 usage: python tools/ncu_traffic.py NSUB stats.ncu-rep spec.ncu-rep [order.ncu-rep] > profiles/ncu_traffic.json
-The output names the sha256 of the libmhb200.so in the tree: bench.py uses the figures only for that very build."""
+The output names the sha256 of the kernel sources in the tree (bench.csrc_sha256): bench.py uses the figures only for
+those very sources."""
 import csv
 import hashlib
 import io
@@ -30,8 +31,9 @@ def traffic(rep):
 def main():
     nsub = int(sys.argv[1])
     st, sp = traffic(sys.argv[2]), traffic(sys.argv[3])
-    lib = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "pymhealth_b200", "libmhb200.so")
-    out = {"subjects_per_gpu": nsub, "lib_sha256": hashlib.sha256(open(lib, "rb").read()).hexdigest(),
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    out = {"subjects_per_gpu": nsub, "csrc_sha256": bench.csrc_sha256(),
            "source": "ncu --set full --clock-control none, one launch each at bench shard size",
            "traffic_bytes_per_launch": {"window_stats": st["dram_read"] + st["dram_write"],
                                         "window_spectral": sp["dram_read"] + sp["dram_write"]},
