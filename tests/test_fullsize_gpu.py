@@ -113,3 +113,43 @@ def test_series_longer_than_2_31_samples():
     with pytest.raises(SystemExit) as ex:
         runpy.run_path(tool, run_name="__main__")
     assert ex.value.code == 0
+
+
+def test_config2_order_statistics_one_subject_week():
+    """Accelerometer 50 Hz x 7 d (30 240 000 samples), W = 500, S = 250: 120 959 windows through the streaming order
+    kernel.  Properties that need no oracle pass: the 0th / 100th percentiles ARE the window extrema (bit for bit against
+    kernel 1a and against a numpy block reduction), quantiles are monotone in q, IQR = p75 - p25, the median is odd under
+    negation and homogeneous under scaling by 2 (both exact), and a sorted-window recomputation of 64 windows
+    picked across the week (chunk boundaries included) reproduces every column."""
+    import torch
+    from pymhealth_b200 import synth, engine
+    from pymhealth_b200.generic import stats
+    n, W, S = 30_240_000, 500, 250
+    x = synth.accelerometer(5, n)[2]
+    xd = torch.from_numpy(x).cuda()
+    qs = [0.0, 10.0, 25.0, 50.0, 75.0, 90.0, 100.0]
+    feats = [stats.percentile.feature(q) for q in qs] + [stats.median.feature(), stats.interquartile_range.feature()]
+    tab = engine.window_table(xd, W, S, feats, out_dtype=torch.float64).cpu().numpy()
+    nw = 1 + (n - W) // S
+    assert tab.shape == (nw, 9)
+    ext = engine.window_table(xd, W, S, [stats.dmin.feature(), stats.dmax.feature()], out_dtype=torch.float64).cpu().numpy()
+    np.testing.assert_array_equal(tab[:, 0], ext[:, 0])
+    np.testing.assert_array_equal(tab[:, 6], ext[:, 1])
+    bmin = x[: (n // S) * S].reshape(-1, S).min(axis=1)
+    np.testing.assert_array_equal(tab[:, 0], np.minimum(bmin[:-1], bmin[1:])[:nw].astype(np.float64))
+    assert np.all(np.diff(tab[:, :7], axis=1) >= 0)                       # monotone in q
+    np.testing.assert_array_equal(tab[:, 7], tab[:, 3])                   # median == p50 (even W: the same two samples, weight 1/2)
+    np.testing.assert_allclose(tab[:, 8], tab[:, 4] - tab[:, 2], rtol=1e-15, atol=0)
+    neg = engine.window_table(-xd, W, S, [stats.median.feature()], out_dtype=torch.float64).cpu().numpy()[:, 0]
+    np.testing.assert_array_equal(neg, -tab[:, 7])
+    # scaling the data by 2 is exact, so every selected sample -- and the interpolation -- scales exactly
+    sc = engine.window_table(xd * 2.0, W, S, [stats.median.feature(), stats.percentile.feature(90.0)],
+                             out_dtype=torch.float64).cpu().numpy()
+    np.testing.assert_array_equal(sc[:, 0], 2.0 * tab[:, 7])
+    np.testing.assert_allclose(sc[:, 1], 2.0 * tab[:, 5], rtol=1e-15, atol=0)
+    pick = np.unique(np.concatenate([np.arange(0, 6), np.arange(124, 132), np.arange(252, 258), [nw - 3, nw - 2, nw - 1],
+                                     np.random.default_rng(3).integers(0, nw, 41)]))
+    for w in pick:
+        seg = x[w * S: w * S + W].astype(np.float64)
+        want = [np.percentile(seg, q) for q in qs] + [np.median(seg), np.percentile(seg, 75) - np.percentile(seg, 25)]
+        np.testing.assert_allclose(tab[w], want, rtol=1e-13, atol=0)
