@@ -93,23 +93,30 @@ __global__ void __launch_bounds__(256, 4) k(float* out, int n_iter, float s) {
 #pragma unroll
             for (int u = 0; u < 16; ++u)
 #pragma unroll
-                for (int i = 0; i < 8; i += 2) {
-                    const float a = v[i], c = v[i ^ 1 ^ (u & 6)];
-                    const float mn = fminf(a, c);
-                    int t, m;
-                    asm("mad.lo.s32 %0, %1, %2, %3;" : "=r"(t) : "r"(__float_as_int(a)), "r"(one), "r"(__float_as_int(c)));
-                    asm("mad.lo.s32 %0, %1, %2, %3;" : "=r"(m) : "r"(__float_as_int(mn)), "r"(mone), "r"(t));
-                    v[i] = mn;
-                    v[i ^ 1 ^ (u & 6)] = __int_as_float(m);
+                for (int i = 0; i < 8; ++i) {
+                    const int j = 1 << (u % 3);
+                    if ((i ^ j) > i) {
+                        const float a = v[i], c = v[i ^ j];
+                        const float mn = fminf(a, c);
+                        int t, m;
+                        asm("mad.lo.s32 %0, %1, %2, %3;" : "=r"(t) : "r"(__float_as_int(a)), "r"(one), "r"(__float_as_int(c)));
+                        asm("mad.lo.s32 %0, %1, %2, %3;" : "=r"(m) : "r"(__float_as_int(mn)), "r"(mone), "r"(t));
+                        v[i] = mn;
+                        v[i ^ j] = __int_as_float(m);
+                    }
                 }
         } else if (MODE == 6) {
+            // distances 1, 2, 4 in turn (the same pair twice in a row would be simplified away by the compiler)
 #pragma unroll
             for (int u = 0; u < 16; ++u)
 #pragma unroll
-                for (int i = 0; i < 8; i += 2) {
-                    const float a = v[i], c = v[i ^ 1 ^ (u & 6)];
-                    v[i] = fminf(a, c);
-                    v[i ^ 1 ^ (u & 6)] = fmaxf(a, c);
+                for (int i = 0; i < 8; ++i) {
+                    const int j = 1 << (u % 3);
+                    if ((i ^ j) > i) {
+                        const float a = v[i], c = v[i ^ j];
+                        v[i] = fminf(a, c);
+                        v[i ^ j] = fmaxf(a, c);
+                    }
                 }
         }
     }
@@ -158,7 +165,7 @@ int main() {
     run<3>("FMNMX(+FFMA) x128", 256, out, n);
     run<4>("FMUL x128", 128, out, n);
     run<5>("FMUL+FMUL+SHFL+FMNMX x128", 512, out, n);
-    run<6>("in-register compare-exchange x64", 128, out, n);
+    run<6>("in-register compare-exchange (2 FMNMX) x64", 128, out, n);
     run<7>("compare-exchange FMNMX + 2 IMAD x64", 192, out, n);
     printf("cudaGetLastError: %s\n", cudaGetErrorString(cudaGetLastError()));
     return 0;
