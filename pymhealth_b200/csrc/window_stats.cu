@@ -235,7 +235,8 @@ __device__ __forceinline__ int wrap(int i, int n) { return i >= n ? i - n : i; }
 
 // ---------------------------------------------------------------------------------------------
 // GEO = 1: the hot geometry (cpb = 10, k = 2, hop = 1, TB = 25 -- W = 500 / S = 250 with 25-sample cells) with every
-// loop bound known at compile time; GEO = 0: bounds from the plan.
+// loop bound known at compile time; GEO = 2: the same for W = 1920 / S = 64 (BASELINE configs[3]: cpb = 4 cells of 16, k = 30,
+// hop = 1, TB = 64); GEO = 0: bounds from the plan.
 // MAG = true: magnitude mode with the three axes staged by TMA side by side (x | y | z, stage_elems apart) and combined
 // as phase 1 reads them; MAG = false with P.y set: the guarded-copy path combines them while copying.
 template <typename InT, typename OutT, bool M4, bool TD, int MCELL /*0 = runtime m; -8 = 2 x float4*/, int GEO, bool MAG = false>
@@ -245,7 +246,8 @@ __global__ void __launch_bounds__(kThreads, 3) window_stats_kernel(const StatsPl
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int tid = threadIdx.x;
     const int m = MCELL > 0 ? MCELL : (MCELL < 0 ? -MCELL : P.m);
-    const int g_cpb = GEO ? 10 : P.cpb, g_k = GEO ? 2 : P.k, g_hop = GEO ? 1 : P.hop, g_TB = GEO ? 25 : P.TB;
+    const int g_cpb = GEO == 1 ? 10 : GEO == 2 ? 4 : P.cpb, g_k = GEO == 1 ? 2 : GEO == 2 ? 30 : P.k, g_hop = GEO ? 1 : P.hop,
+              g_TB = GEO == 1 ? 25 : GEO == 2 ? 64 : P.TB;
     using Part = Partials<InT, M4, TD>;
 
     // ---- carve shared memory
@@ -761,7 +763,10 @@ cudaError_t launch_with_cell(const StatsPlan& P, int mt, dim3 grid, size_t smem,
         if constexpr (sizeof(InT) == 4) MHB_LAUNCH(-8, 0)
     }
     if (mt == -16) {
-        if constexpr (sizeof(InT) == 4) MHB_LAUNCH(-16, 0)
+        if constexpr (sizeof(InT) == 4) {
+            if (P.cpb == 4 && P.k == 30 && P.hop == 1 && P.TB == 64 && getenv("MHB_STATS_NOGEO2") == nullptr) MHB_LAUNCH(-16, 2)
+            MHB_LAUNCH(-16, 0)
+        }
     }
     if (mt == 25) {
         if (P.cpb == 10 && P.k == 2 && P.hop == 1 && P.TB == 25) MHB_LAUNCH(25, 1)
