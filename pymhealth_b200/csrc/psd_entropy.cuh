@@ -15,6 +15,16 @@ namespace mhb {
 
 constexpr float kToneEntropy = 0.1f;
 
+// log2 of a NORMAL float32 (>= 2^-126): one MUFU.LG2.  `__log2f` carries the denormal fix-up around it (FSETP, FMUL by
+// 2^24, FSEL before, a predicated FADD -24 after): four more instructions per bin, two of them on the half-rate ALU pipe --
+// 7 % of the W = 500 kernel's instructions in ncu.  Every per-bin argument of the entropy sums is offset by >= 1e-37 before
+// the logarithm, so the flush-to-zero form is exact for them (same MUFU result).
+__device__ __forceinline__ float log2_normal(float x) {
+    float r;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
 // A kernel that has no PSD row left when it finds such a window (spectral_w1920.cu) stores this quiet-NaN bit pattern
 // in the window's entropy cells instead; window_spectral_kernel, run afterwards in redo mode, re-evaluates the marked
 // windows with the formula below.  (An all-zero window's entropy is an ordinary NaN, not this pattern.)

@@ -350,7 +350,7 @@ __device__ __forceinline__ void pass_b(const C* __restrict__ bw, const C* __rest
         // + 1e-37: y log2 y -> 0 for an empty bin without a compare (the offset is 2^-123 against y = O(1) for every bin
         // that matters, far below float32 resolution)
         const float2 y = __ffma2_rn(psd[i], make_float2(scale, scale), make_float2(1e-37f, 1e-37f));
-        hh = __ffma2_rn(y, make_float2(__log2f(y.x), __log2f(y.y)), hh);
+        hh = __ffma2_rn(y, make_float2(log2_normal(y.x), log2_normal(y.y)), hh);
     }
     const int q = w * kNP + p;
     const_cast<float*>(R.ptot)[q] = tot;

@@ -326,8 +326,8 @@ __global__ void __launch_bounds__(kT, kCtasPerSM) spectral_w1920_kernel(const Pl
 #pragma unroll
                 for (int i = 0; i < 20; i += 2) {
                     const float y1 = psd[i] * scale, y2 = psd[i + 1] * scale;
-                    ha = fmaf(y1, __log2f(fmaxf(y1, 1e-37f)), ha);
-                    hb = fmaf(y2, __log2f(fmaxf(y2, 1e-37f)), hb);
+                    ha = fmaf(y1, log2_normal(fmaxf(y1, 1e-37f)), ha);
+                    hb = fmaf(y2, log2_normal(fmaxf(y2, 1e-37f)), hb);
                 }
                 const int q = w * kNP + p;
                 rec_tot[q] = tot;

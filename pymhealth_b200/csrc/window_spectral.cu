@@ -193,12 +193,12 @@ __global__ void __launch_bounds__(kWarps * 32) window_spectral_kernel(const Spec
                 int k = lane == 0 ? 32 : lane;
                 for (; k + 32 < P.nb; k += 64) {
                     const float p = fmaf(psd[k], inv, 1e-30f), p2 = fmaf(psd[k + 32], inv, 1e-30f);
-                    h0 = fmaf(p, __log2f(p), h0);
-                    h1 = fmaf(p2, __log2f(p2), h1);
+                    h0 = fmaf(p, log2_normal(p), h0);
+                    h1 = fmaf(p2, log2_normal(p2), h1);
                 }
                 if (k < P.nb) {
                     const float p = fmaf(psd[k], inv, 1e-30f);
-                    h0 = fmaf(p, __log2f(p), h0);
+                    h0 = fmaf(p, log2_normal(p), h0);
                 }
                 double hs = warp_sum(static_cast<double>((h0 + h1) * 0.69314718055994530942f));
                 const double p0 = dc / tot + 1e-30, qrest = (tot - dc) / tot;
