@@ -320,8 +320,12 @@ __device__ __forceinline__ void pass_b(const C* __restrict__ bw, const C* __rest
         const float2 e = __fadd2_rn(f2(zk), make_float2(zn.x, -zn.y));
         const C o = cx(__fadd2_rn(make_float2(zk.y, -zk.x), make_float2(zn.y, zn.x)));
         const C t = cmul(o, t2);
-        const float2 re = __fadd2_rn(make_float2(e.x, e.x), make_float2(t.x, -t.x));     // (Re X[k], Re X[N - k])
-        const float2 im = __fadd2_rn(make_float2(e.y, e.y), make_float2(t.y, -t.y));
+        // (Re X[k], Re X[N - k]) = e.x +- t.x as ONE packed FMA (1, -1) * t.x + e.x with both scalars as broadcast operands
+        // (same roundings as the two additions); a packed add of (e.x, e.x) and (t.x, -t.x) needs the second pair built
+        // with two MOVs first
+        const float2 pm = make_float2(1.f, -1.f);
+        const float2 re = __ffma2_rn(pm, make_float2(t.x, t.x), make_float2(e.x, e.x));
+        const float2 im = __ffma2_rn(pm, make_float2(t.y, t.y), make_float2(e.y, e.y));
         psd[k2] = __ffma2_rn(re, re, __fmul2_rn(im, im));
         if (!P0 || k2 == 0) hi_ptr[-25 * k2] = psd[k2].y;      // P0: bin N; the other high-set bins belong to the low set
         if (!P0 || k2 > 0) lo_ptr[25 * k2] = psd[k2].x;
@@ -502,7 +506,10 @@ __global__ void __launch_bounds__(kThreadsF, 3) spectral_fast_kernel(const FastP
                 }
                 dft25(a);
                 C* dst = buf + w * kWSB + n2 * 25;
-                dst[0] = a[0];
+                auto st = [](C* q, C v) {      // plain STS.64 from the register pair the product was formed in
+                    asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(smem_u32(q)), "f"(v.x), "f"(v.y) : "memory");
+                };
+                st(dst, a[0]);
                 // w250^(n2 k1); the n2 = 0 threads multiply by the table's exact (1, 0) (they share their warps with
                 // n2 = 1: a separate copy loop would only add a divergent path)
                 const C* tw = twA + n2;
@@ -512,7 +519,7 @@ __global__ void __launch_bounds__(kThreadsF, 3) spectral_fast_kernel(const FastP
 #pragma unroll
                     for (int u = 0; u < 6; ++u) t[u] = tw[(k0 + u) * kNA];
 #pragma unroll
-                    for (int u = 0; u < 6; ++u) dst[k0 + u] = cmul(a[k0 + u], t[u]);
+                    for (int u = 0; u < 6; ++u) st(dst + k0 + u, cmul(a[k0 + u], t[u]));
                 }
                 if (n2 == 0) piv[w] = m;
             }
