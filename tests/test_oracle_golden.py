@@ -188,3 +188,36 @@ def test_oracle_min_max_propagate_nan_like_numba():
             w[rng.integers(0, 17)] = np.nan
         lo, hi = ref(w)
         np.testing.assert_array_equal([OR.w_min(w), OR.w_max(w)], [lo, hi])
+
+
+def test_location_extensions_against_independent_implementations():
+    """The north-star's extensions (radius of gyration, stay points) have no reference implementation, so
+    oracle/location_ext.py is their definition ("parity unpinned").  What CAN be pinned: the radius of gyration against
+    scikit-learn's great-circle distance (an independent implementation of the same haversine formula), and the
+    stay-point scan against a plain-Python restatement of the published anchor scan written from the docstring alone."""
+    import math
+    from sklearn.metrics.pairwise import haversine_distances
+    from pymhealth_b200 import synth
+    from oracle import location_ext as OX
+    lat, lon, t, _ = synth.gps(3, 4000, 60)
+    r_km = 12742.018 / 2.0                                    # location/distance.py:8,18
+    c = np.radians([[lat.mean(), lon.mean()]])
+    d = haversine_distances(np.radians(np.stack([lat, lon], axis=1)), c)[:, 0] * r_km
+    np.testing.assert_allclose(OX.radius_of_gyration(lat, lon), math.sqrt(np.mean(d * d)), rtol=1e-9)
+
+    def hav(a1, o1, a2, o2):
+        a1, o1, a2, o2 = map(math.radians, (a1, o1, a2, o2))
+        h = math.sin((a2 - a1) / 2) ** 2 + math.cos(a1) * math.cos(a2) * math.sin((o2 - o1) / 2) ** 2
+        return 2 * r_km * math.asin(math.sqrt(h))
+    for dist_km, min_dur in ((0.2, 1800), (0.05, 600), (1.0, 7200)):
+        want = np.full(len(lat), -1, dtype=np.int64)
+        i = k = 0
+        while i < len(lat):
+            j = i + 1
+            while j < len(lat) and hav(lat[i], lon[i], lat[j], lon[j]) <= dist_km:
+                j += 1
+            if t[j - 1] - t[i] >= min_dur:
+                want[i:j] = k
+                k += 1
+            i = j
+        np.testing.assert_array_equal(OX.stay_points(lat, lon, t, dist_km, min_dur), want)
