@@ -25,7 +25,7 @@ def test_index_window_count_integers(first, span, step):
 
 
 @settings(max_examples=200, deadline=None)
-@given(first=st.floats(-1e6, 1e6), span=st.floats(0, 1e5), step=st.floats(1e-3, 1e4))
+@given(first=st.floats(-1e6, 1e6), span=st.floats(0, 1e3), step=st.floats(1e-3, 1e4))      # <= 1e6 keys per case
 def test_index_window_count_floats(first, span, step):
     from pymhealth_b200 import engine
     assert engine.n_index_windows(first, first + span, step, True) == len(np.arange(first, first + span, step))
